@@ -1,0 +1,246 @@
+// GroupNorm(32) [+SiLU] and LayerNorm for channels-last fp16 activations.  Statistics in fp32 (final
+// combine in fp64), matching the reference's fp32 GroupNorm32 / autocast-fp32 LayerNorm.
+#include "common.cuh"
+
+namespace hi3d {
+
+constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_GROUPS = 32;
+
+// ---- pass 1: per-(sample, chunk, group) partial sum / sum of squares -------------------------------
+// grid (chunks, n_samples); blockDim = RL * CV where CV = C/8 vector-columns, so every thread owns one
+// fixed 8-channel column and walks rows with stride RL.
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
+                long long rows_per_chunk, float* __restrict__ ws) {
+  __shared__ float sg[GN_GROUPS * 2];
+  const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
+  const int tid = threadIdx.x;
+  if (tid < GN_GROUPS * 2) sg[tid] = 0.f;
+  __syncthreads();
+  const int cv = tid % CV, rl = tid / CV, RL = blockDim.x / CV;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const long long r0 = (long long)chunk * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  const int c0 = cv * 8;
+  const __half* base;
+  int ld;
+  if (c0 < C1) { base = x1 + c0; ld = C1; } else { base = x2 + (c0 - C1); ld = C2; }
+  base += (long long)n * rows_per_sample * ld;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) s[e] = q[e] = 0.f;
+  for (long long r = r0 + rl; r < r1; r += RL) {
+    const Half8 v = *reinterpret_cast<const Half8*>(base + r * ld);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 f = __half22float2(v.h[k]);
+      s[2 * k] += f.x; q[2 * k] += f.x * f.x;
+      s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
+    }
+  }
+  // fold the 8 channels into their groups (a vector may straddle a group boundary when cpg % 8 != 0)
+  int gcur = c0 / cpg;
+  float as = 0.f, aq = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const int gi = (c0 + e) / cpg;
+    if (gi != gcur) {
+      atomicAdd(&sg[2 * gcur], as); atomicAdd(&sg[2 * gcur + 1], aq);
+      as = aq = 0.f; gcur = gi;
+    }
+    as += s[e]; aq += q[e];
+  }
+  atomicAdd(&sg[2 * gcur], as); atomicAdd(&sg[2 * gcur + 1], aq);
+  __syncthreads();
+  if (tid < GN_GROUPS * 2) ws[((long long)n * GN_MAX_CHUNKS + chunk) * (GN_GROUPS * 2) + tid] = sg[tid];
+}
+
+// ---- pass 2: y = [silu]((x - mean) * rstd * gamma + beta) ------------------------------------------
+// grid (row_slabs, n_samples). Dynamic smem: 2*C floats (per-channel scale / shift).
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
+                int rows_per_cta, int nchunks, const float* __restrict__ ws, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int apply_silu, __half* __restrict__ y) {
+  extern __shared__ float sm[];
+  __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+  const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
+  float* sA = sm;
+  float* sB = sm + C;
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (tid < GN_GROUPS) {
+    double s = 0.0, q = 0.0;
+    const float* w = ws + (long long)n * GN_MAX_CHUNKS * (GN_GROUPS * 2) + 2 * tid;
+    for (int c = 0; c < nchunks; c++) { s += (double)w[c * (GN_GROUPS * 2)]; q += (double)w[c * (GN_GROUPS * 2) + 1]; }
+    const double cnt = (double)rows_per_sample * (double)cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    smean[tid] = (float)mean;
+    srstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    const int g = c / cpg;
+    const float a = srstd[g] * gamma[c];
+    sA[c] = a;
+    sB[c] = beta[c] - smean[g] * a;
+  }
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long nrows = rows_per_sample - r0;
+  if (nrows > rows_per_cta) nrows = rows_per_cta;
+  const long long total = nrows * CV;
+  const long long srow0 = (long long)n * rows_per_sample + r0;
+  for (long long idx = tid; idx < total; idx += 256) {
+    const long long r = idx / CV;
+    const int cv = (int)(idx - r * CV);
+    const int c0 = cv * 8;
+    const __half* src = (c0 < C1) ? x1 + (srow0 + r) * C1 + c0 : x2 + (srow0 + r) * C2 + (c0 - C1);
+    Half8 v = *reinterpret_cast<const Half8*>(src);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float2 f = __half22float2(v.h[k]);
+      f.x = f.x * sA[c0 + 2 * k] + sB[c0 + 2 * k];
+      f.y = f.y * sA[c0 + 2 * k + 1] + sB[c0 + 2 * k + 1];
+      if (apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+      v.h[k] = __floats2half2_rn(f.x, f.y);
+    }
+    *reinterpret_cast<Half8*>(y + (srow0 + r) * C + c0) = v;
+  }
+}
+
+// ---- LayerNorm: one warp per row, row kept in registers ----------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ addvec, int add_div, int add_mod, long long M,
+                 int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 __half* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int CV = C >> 3;
+  const __half* row = x + m * C;
+  const __half* av = addvec ? addvec + (long long)((m / add_div) % add_mod) * C : nullptr;
+  float v[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int cv = lane + 32 * i;
+    if (cv < CV) {
+      const Half8 h = *reinterpret_cast<const Half8*>(row + cv * 8);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(h.h[k]);
+        v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+      }
+      if (av) {
+        const Half8 a = *reinterpret_cast<const Half8*>(av + cv * 8);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float2 f = __half22float2(a.h[k]);
+          v[i][2 * k] += f.x; v[i][2 * k + 1] += f.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) sum += v[i][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[i][e] = 0.f;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    if (lane + 32 * i < CV) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int cv = lane + 32 * i;
+    if (cv < CV) {
+      Half8 o;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = cv * 8 + 2 * k;
+        o.h[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * gamma[c] + beta[c],
+                                   (v[i][2 * k + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+      }
+      *reinterpret_cast<Half8*>(y + m * C + cv * 8) = o;
+    }
+  }
+}
+
+}  // namespace hi3d
+
+using namespace hi3d;
+
+extern "C" int64_t hi3d_groupnorm_ws_floats(int n_samples) {
+  return (int64_t)n_samples * GN_MAX_CHUNKS * GN_GROUPS * 2;
+}
+
+extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples,
+                                   int64_t rows_per_sample, const float* gamma, const float* beta, float eps,
+                                   int apply_silu, void* y, float* ws, void* stream) {
+  const int C = C1 + (x2 ? C2 : 0);
+  if (!x2) C2 = 0;
+  if (!x1 || !y || !ws || !gamma || !beta || n_samples <= 0 || rows_per_sample <= 0 || C1 <= 0 || (C1 % 8) || (C2 % 8) ||
+      (C % GN_GROUPS) || C > 4096 || ((uintptr_t)x1 & 15) || ((uintptr_t)y & 15) || (x2 && ((uintptr_t)x2 & 15)) ||
+      n_samples > 65535) {
+    set_error("hi3d_groupnorm_silu: bad arguments (C1=%d C2=%d n=%d rows=%lld)", C1, C2, n_samples,
+              (long long)rows_per_sample);
+    return -2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int CV = C / 8;
+  const int threads = (512 / CV) * CV;
+  const int RL = threads / CV;
+  // enough CTAs for a few waves, each chunk at least a handful of row-lanes deep
+  long long chunks = (592 + n_samples - 1) / n_samples;
+  const long long max_by_rows = (rows_per_sample + (long long)RL * 4 - 1) / ((long long)RL * 4);
+  if (chunks > max_by_rows) chunks = max_by_rows;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  long long rpc = (rows_per_sample + chunks - 1) / chunks;
+  chunks = (rows_per_sample + rpc - 1) / rpc;
+  gn_stats_kernel<<<dim3((unsigned)chunks, n_samples), threads, 0, st>>>((const __half*)x1, C1, (const __half*)x2, C2,
+                                                                        rows_per_sample, rpc, ws);
+  int rc = check_launch("hi3d_groupnorm_silu(stats)");
+  if (rc) return rc;
+  int rows_per_cta = 4096 / CV;
+  if (rows_per_cta < 1) rows_per_cta = 1;
+  const long long slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
+  if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_silu: too many slabs"); return -2; }
+  gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), 256, 2 * C * sizeof(float), st>>>(
+      (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, (int)chunks, ws, gamma, beta, eps,
+      apply_silu, (__half*)y);
+  return check_launch("hi3d_groupnorm_silu(apply)");
+}
+
+extern "C" int hi3d_layernorm(const void* x, const void* addvec, int add_div, int add_mod, int64_t M, int C,
+                              const float* gamma, const float* beta, float eps, void* y, void* stream) {
+  if (!x || !y || !gamma || !beta || M <= 0 || C <= 0 || (C % 8) || C > 2560 || ((uintptr_t)x & 15) ||
+      ((uintptr_t)y & 15) || (addvec && (add_div <= 0 || add_mod <= 0 || ((uintptr_t)addvec & 15)))) {
+    set_error("hi3d_layernorm: bad arguments (M=%lld C=%d)", (long long)M, C);
+    return -2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long blocks = (M + 7) / 8;
+  if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }
+  const int CV = C / 8;
+  if (CV <= 64)
+    layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)addvec, add_div, add_mod, M, C,
+                                                         gamma, beta, eps, (__half*)y);
+  else if (CV <= 160)
+    layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)addvec, add_div, add_mod, M, C,
+                                                         gamma, beta, eps, (__half*)y);
+  else
+    layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)addvec, add_div, add_mod, M,
+                                                          C, gamma, beta, eps, (__half*)y);
+  return check_launch("hi3d_layernorm");
+}

@@ -1,0 +1,232 @@
+"""Thin typed wrappers that turn torch CUDA tensors into C-ABI calls (pointers + sizes + stream).
+
+torch is used for device memory and streams only; every function here ends in exactly one
+`libhi3d_b200.so` entry point and raises if that fails.  `Gemm` pre-bakes its parameter block once so a
+replayed step costs one ctypes call per launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+from ._native import ACT_GEGLU, ACT_NONE, ACT_SILU, ROWS_CONV2D, ROWS_PLAIN, ROWS_TEMPORAL  # noqa: F401
+
+F16 = torch.float16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk16(t: torch.Tensor, name: str):
+    if t.dtype != F16 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA fp16 tensor, got {t.dtype} {t.device} "
+                         f"contiguous={t.is_contiguous()}")
+
+
+def _chk32(t: torch.Tensor, name: str):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA fp32 tensor")
+
+
+class SegSpec:
+    """One K-segment of the implicit-GEMM A operand (see hi3d_seg)."""
+    __slots__ = ("src", "ld", "c_off", "C", "dy", "dx", "dt")
+
+    def __init__(self, src: torch.Tensor, C_: Optional[int] = None, c_off: int = 0, dy: int = 0, dx: int = 0,
+                 dt: int = 0, ld: Optional[int] = None):
+        _chk16(src, "segment source")
+        self.src = src
+        self.ld = src.shape[-1] if ld is None else ld
+        self.C = (self.ld - c_off) if C_ is None else C_
+        self.c_off, self.dy, self.dx, self.dt = c_off, dy, dx, dt
+
+
+def conv_taps(srcs: Sequence[torch.Tensor], pad_lo: int = 1, ksize: int = 3) -> List[SegSpec]:
+    """Segments of a kxk conv over the channel-concat of `srcs`: tap-major, source-minor -- the K order of
+    weight.permute(0, 2, 3, 1) of a conv whose input channels are [srcs[0] | srcs[1] | ...]."""
+    segs = []
+    for ky in range(ksize):
+        for kx in range(ksize):
+            for s in srcs:
+                segs.append(SegSpec(s, dy=ky - pad_lo, dx=kx - pad_lo))
+    return segs
+
+
+def temporal_taps(src: torch.Tensor) -> List[SegSpec]:
+    return [SegSpec(src, dt=d) for d in (-1, 0, 1)]
+
+
+class Gemm:
+    """out[M, N(/2)] = epilogue(A_gather[M, K] @ W[N, K]^T): one pre-baked hi3d_gemm_params block."""
+
+    def __init__(self, segs: Sequence[SegSpec], W: torch.Tensor, out: torch.Tensor, M: int, *, mode: int = ROWS_PLAIN,
+                 geom: Optional[dict] = None, bias: Optional[torch.Tensor] = None,
+                 rowbias: Optional[torch.Tensor] = None, rb_div: int = 1, rb_mod: int = 1, act: int = ACT_NONE,
+                 residual: Optional[torch.Tensor] = None, blend_x: Optional[torch.Tensor] = None, alpha: float = 0.0,
+                 engine: str = "mma"):
+        _chk16(W, "W")
+        _chk16(out, "out")
+        Nn, K = W.shape
+        if len(segs) > N.MAX_SEGS:
+            raise ValueError(f"too many segments ({len(segs)})")
+        p = N.GemmParams()
+        p.M, p.N, p.K, p.mode = M, Nn, K, mode
+        g = geom or {}
+        p.Ho, p.Wo = g.get("Ho", 1), g.get("Wo", 1)
+        p.Hs, p.Ws = g.get("Hs", p.Ho), g.get("Ws", p.Wo)
+        p.stride, p.ups, p.T = g.get("stride", 1), g.get("ups", 0), g.get("T", 1)
+        p.nseg = len(segs)
+        for i, s in enumerate(segs):
+            p.seg[i].src, p.seg[i].ld, p.seg[i].c_off, p.seg[i].C = s.src.data_ptr(), s.ld, s.c_off, s.C
+            p.seg[i].dy, p.seg[i].dx, p.seg[i].dt = s.dy, s.dx, s.dt
+        p.W = W.data_ptr()
+        if bias is not None:
+            _chk32(bias, "bias")
+            if bias.numel() != Nn:
+                raise ValueError("bias size")
+        p.bias = _ptr(bias)
+        if rowbias is not None:
+            _chk16(rowbias, "rowbias")
+            p.rb_ld = rowbias.shape[-1]
+        p.rowbias, p.rb_div, p.rb_mod = _ptr(rowbias), rb_div, rb_mod
+        p.act = act
+        n_out = Nn // 2 if act == ACT_GEGLU else Nn
+        if residual is not None:
+            _chk16(residual, "residual")
+            p.res_ld = residual.shape[-1]
+        p.residual = _ptr(residual)
+        if blend_x is not None:
+            _chk16(blend_x, "blend_x")
+            p.blend_ld = blend_x.shape[-1]
+        p.blend_x, p.alpha = _ptr(blend_x), float(alpha)
+        p.out, p.out_ld = out.data_ptr(), out.shape[-1]
+        if out.shape[-1] < n_out or out.numel() < M * out.shape[-1]:
+            raise ValueError(f"out too small: {tuple(out.shape)} for M={M} N_out={n_out}")
+        self.p = p
+        self._keep = (list(segs), W, out, bias, rowbias, residual, blend_x)   # keep storages alive
+        self._fn = N.load().hi3d_gemm_tc5 if engine == "tc5" else N.load().hi3d_gemm
+        self.flops = 2.0 * M * Nn * K
+        self.out = out
+
+    def __call__(self):
+        rc = self._fn(C.byref(self.p), _stream())
+        if rc:
+            N.check(rc, "hi3d_gemm")
+
+
+# ------------------------------------------------------------------------------------------------------
+def groupnorm_ws(n_samples: int, device) -> torch.Tensor:
+    return torch.empty(int(N.load().hi3d_groupnorm_ws_floats(n_samples)), dtype=torch.float32, device=device)
+
+
+def groupnorm_silu(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int, rows_per_sample: int,
+                   gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, y: torch.Tensor,
+                   ws: torch.Tensor):
+    _chk16(x1, "x1"); _chk16(y, "y"); _chk32(gamma, "gamma"); _chk32(beta, "beta")
+    c2 = 0
+    if x2 is not None:
+        _chk16(x2, "x2")
+        c2 = x2.shape[-1]
+    N.check(N.load().hi3d_groupnorm_silu(x1.data_ptr(), x1.shape[-1], _ptr(x2), c2, n_samples, rows_per_sample,
+                                         gamma.data_ptr(), beta.data_ptr(), eps, int(silu), y.data_ptr(),
+                                         ws.data_ptr(), _stream()), "hi3d_groupnorm_silu")
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, M: int,
+              addvec: Optional[torch.Tensor] = None, add_div: int = 1, add_mod: int = 1, eps: float = 1e-5):
+    _chk16(x, "x"); _chk16(y, "y"); _chk32(gamma, "gamma"); _chk32(beta, "beta")
+    if addvec is not None:
+        _chk16(addvec, "addvec")
+    N.check(N.load().hi3d_layernorm(x.data_ptr(), _ptr(addvec), add_div, add_mod, M, x.shape[-1], gamma.data_ptr(),
+                                    beta.data_ptr(), eps, y.data_ptr(), _stream()), "hi3d_layernorm")
+
+
+def attention_d64(qkv: torch.Tensor, n_img: int, L: int, heads: int, out: torch.Tensor, scale: float = 0.125):
+    _chk16(qkv, "qkv"); _chk16(out, "out")
+    N.check(N.load().hi3d_attention_d64(qkv.data_ptr(), n_img, L, heads, scale, out.data_ptr(), _stream()),
+            "hi3d_attention_d64")
+
+
+def temporal_attention_d64(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, out: torch.Tensor,
+                           scale: float = 0.125):
+    _chk16(qkv, "qkv"); _chk16(out, "out")
+    N.check(N.load().hi3d_temporal_attention_d64(qkv.data_ptr(), B, T, S, heads, scale, out.data_ptr(), _stream()),
+            "hi3d_temporal_attention_d64")
+
+
+def softmax_rows(s: torch.Tensor, rows: int, L: int, scale: float):
+    _chk16(s, "s")
+    N.check(N.load().hi3d_softmax_rows(s.data_ptr(), rows, L, scale, _stream()), "hi3d_softmax_rows")
+
+
+def transpose(x: torch.Tensor, R: int, Cc: int, in_ld: int, out: torch.Tensor):
+    N.check(N.load().hi3d_transpose(x.data_ptr(), R, Cc, in_ld, out.data_ptr(), _stream()), "hi3d_transpose")
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: torch.Tensor, max_period: float = 10000.0):
+    _chk32(t, "t"); _chk16(out, "out")
+    N.check(N.load().hi3d_timestep_embedding(t.data_ptr(), t.numel(), dim, max_period, out.data_ptr(), _stream()),
+            "hi3d_timestep_embedding")
+
+
+def sampler_pre(x: torch.Tensor, sigma: torch.Tensor, concat_uc: Optional[torch.Tensor], concat_c: Optional[torch.Tensor],
+                out: torch.Tensor):
+    _chk32(x, "x"); _chk32(sigma, "sigma"); _chk16(out, "out")
+    F_, Cx, H, W = x.shape
+    Cc, is32 = 0, 0
+    if concat_c is not None:
+        Cc = concat_c.shape[1]
+        is32 = int(concat_c.dtype == torch.float32)
+        for t in (concat_c, concat_uc):
+            if t is not None and (not t.is_contiguous() or t.dtype != concat_c.dtype or tuple(t.shape) != (F_, Cc, H, W)):
+                raise ValueError("concat tensors must be contiguous NCHW of identical dtype/shape [F, Cc, H, W]")
+    N.check(N.load().hi3d_sampler_pre(x.data_ptr(), sigma.data_ptr(), _ptr(concat_uc), _ptr(concat_c), is32, F_, Cx, Cc,
+                                      H, W, out.shape[-1], out.data_ptr(), _stream()), "hi3d_sampler_pre")
+
+
+def sampler_post(net: torch.Tensor, x: torch.Tensor, sigma: torch.Tensor, sigma_next: torch.Tensor,
+                 scale: torch.Tensor, x_out: torch.Tensor, denoised_out: Optional[torch.Tensor] = None):
+    _chk16(net, "net"); _chk32(x, "x"); _chk32(sigma, "sigma"); _chk32(sigma_next, "sigma_next"); _chk32(scale, "scale")
+    F_, Cx, H, W = x.shape
+    N.check(N.load().hi3d_sampler_post(net.data_ptr(), net.shape[-1], x.data_ptr(), sigma.data_ptr(),
+                                       sigma_next.data_ptr(), scale.data_ptr(), scale.numel(), F_, Cx, H, W,
+                                       x_out.data_ptr(), _ptr(denoised_out), _stream()), "hi3d_sampler_post")
+
+
+def renoise_blend(lat: torch.Tensor, init: torch.Tensor, z: torch.Tensor, alpha: float, sigma: float):
+    _chk32(lat, "lat"); _chk32(init, "init"); _chk32(z, "z")
+    N.check(N.load().hi3d_renoise_blend(lat.data_ptr(), init.data_ptr(), z.data_ptr(), alpha, sigma, lat.numel(),
+                                        _stream()), "hi3d_renoise_blend")
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    if not x.is_contiguous() or x.dtype not in (torch.float32, F16):
+        raise ValueError("nchw_to_nhwc: contiguous fp32/fp16 NCHW expected")
+    n, c, h, w = x.shape
+    _chk16(out, "out")
+    N.check(N.load().hi3d_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.float32), n, c, h, w, out.shape[-1], scale,
+                                       out.data_ptr(), _stream()), "hi3d_nchw_to_nhwc")
+
+
+def nhwc_to_nchw(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    _chk16(x, "x")
+    n, c, h, w = out.shape
+    N.check(N.load().hi3d_nhwc_to_nchw(x.data_ptr(), x.shape[-1], n, c, h, w, scale, out.data_ptr(),
+                                       int(out.dtype == torch.float32), _stream()), "hi3d_nhwc_to_nchw")
+
+
+def gaussian_sample(moments: torch.Tensor, noise: Optional[torch.Tensor], out: torch.Tensor, scale: float):
+    _chk16(moments, "moments"); _chk32(out, "out")
+    n, c, h, w = out.shape
+    if noise is not None:
+        _chk32(noise, "noise")
+    N.check(N.load().hi3d_gaussian_sample(moments.data_ptr(), moments.shape[-1], _ptr(noise), n, c, h, w, scale,
+                                          out.data_ptr(), _stream()), "hi3d_gaussian_sample")

@@ -1,0 +1,57 @@
+"""Weight re-packing from the reference state_dict layout (OIHW convs, [out, in] linears) into the fp16
+K-major [N, K] matrices the implicit-GEMM engine consumes.  Done once at load time."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+F16 = torch.float16
+
+
+def _pad_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def pack_conv2d(w: torch.Tensor, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None) -> torch.Tensor:
+    """(Co, Ci, kh, kw) -> fp16 [Co_p, kh*kw*Ci_p], K ordered (ky, kx, ci) == ops.conv_taps order."""
+    co, ci, kh, kw = w.shape
+    cip = cin_pad or ci
+    cop = cout_pad or co
+    out = torch.zeros(cop, kh, kw, cip, dtype=torch.float32, device=w.device)
+    out[:co, :, :, :ci] = w.float().permute(0, 2, 3, 1)
+    return out.reshape(cop, kh * kw * cip).to(F16).contiguous()
+
+
+def pack_conv3d_t(w: torch.Tensor) -> torch.Tensor:
+    """(Co, Ci, 3, 1, 1) temporal conv -> fp16 [Co, 3*Ci], K ordered (kt, ci) == ops.temporal_taps order."""
+    co, ci = w.shape[:2]
+    return w.float()[:, :, :, 0, 0].permute(0, 2, 1).reshape(co, 3 * ci).to(F16).contiguous()
+
+
+def pack_linear(w: torch.Tensor, cout_pad: Optional[int] = None) -> torch.Tensor:
+    w = w.float().reshape(w.shape[0], -1)
+    if cout_pad and cout_pad > w.shape[0]:
+        w = torch.cat([w, w.new_zeros(cout_pad - w.shape[0], w.shape[1])], 0)
+    return w.to(F16).contiguous()
+
+
+def pack_bias(b: Optional[torch.Tensor], n: int, cout_pad: Optional[int] = None, device=None) -> torch.Tensor:
+    out = torch.zeros(cout_pad or n, dtype=torch.float32, device=device if b is None else b.device)
+    if b is not None:
+        out[:n] = b.float()
+    return out.contiguous()
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GEGLU projection (attention.py:87-94): rows [value(4C) ; gate(4C)] -> interleaved (value_j, gate_j) so
+    the pair lands in one accumulator fragment and x*gelu(gate) is thread-local in the epilogue."""
+    inner = w.shape[0] // 2
+    wi = torch.stack([w[:inner].float(), w[inner:].float()], dim=1).reshape(2 * inner, -1)
+    bi = torch.stack([b[:inner].float(), b[inner:].float()], dim=1).reshape(2 * inner)
+    return wi.to(F16).contiguous(), bi.contiguous()
+
+
+def cat_k(*mats: torch.Tensor) -> torch.Tensor:
+    """Concatenate packed matrices along K (e.g. [3x3 conv | 1x1 skip] fused into one GEMM)."""
+    return torch.cat(mats, dim=1).contiguous()

@@ -1,0 +1,178 @@
+/*
+ * hi3d_b200.h -- C ABI of libhi3d_b200.so: the B200 (sm_100a) kernels behind the Hi3D denoising hot path.
+ *
+ * Boundary: the reference is pure Python/PyTorch; its "FFI" for this path is the set of
+ * ATen / cuDNN / cuBLAS / xformers calls its nn.Modules make.  Each entry point below replaces one such
+ * call site (cited as reference file:line, relative to the Hi3D-Official tree) and is what a maintainer
+ * of the reference would bind with ctypes/cffi (stub shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - activations are fp16, channels-last: a feature map is [N, H, W, C] == a token matrix [N*H*W, C];
+ *     frames of a clip are consecutive samples, n = b*T + t (reference "(b t)" order, video_model.py:71).
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*): no allocation, no
+ *     host synchronisation, safe to capture in a CUDA graph.  Workspaces are caller-owned.
+ *   - return 0 on success, negative on error; hi3d_last_error() returns a thread-local message.
+ */
+#ifndef HI3D_B200_H_
+#define HI3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HI3D_MAX_SEGS 24
+
+/* library ------------------------------------------------------------------------------------ */
+int hi3d_abi_version(void);
+const char* hi3d_last_error(void);
+/* Number of kernels this library has launched since load (for bench.py's `gpu_launches`). */
+int64_t hi3d_launch_count(void);
+/* sm count etc. of the current device (cached).  Returns 0 or negative error. */
+int hi3d_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
+
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM engine.  out[M, N] = epilogue( A[M, K] * W[N, K]^T )
+ *
+ * A is never materialised: its K axis is a list of segments, each a (tap, channel-range) view of an
+ * NHWC fp16 tensor.  This one entry point replaces, in the reference:
+ *   nn.Linear                      attention.py:272-278 (to_q/k/v/out), :90 (GEGLU proj), :109 (ff out),
+ *                                  video_attention.py:221-223 (time_pos_embed), openaimodel.py:286 (emb)
+ *   nn.Conv2d 3x3 s1/s2, 1x1       openaimodel.py:135,192,260,297,314; model.py:63,82,110,117,127
+ *   nearest-x2 + Conv2d            openaimodel.py:154-156; model.py:67-70     (ups = 1)
+ *   F.pad(0,1,0,1) + Conv2d s2 p0  model.py:84-88                              (taps dy,dx in {0,1,2})
+ *   nn.Conv3d (3,1,1)              openaimodel.py:260,297 with dims=3 via video_model.py:42-55 (mode 2)
+ *   th.cat([h, hs.pop()], 1)       video_model.py:491  (two segments per tap = virtual concat)
+ *   skip_connection 1x1 / nin_shortcut   openaimodel.py:314,354; model.py:127,149 (extra K segments)
+ * and in the epilogue: + bias, + emb[:, :, None, None] (openaimodel.py:352), residual adds
+ * (attention.py:551-572), GEGLU x*gelu(gate) (attention.py:92-94), AlphaBlender (util.py:358-369).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* src;   /* fp16 NHWC source tensor                                            */
+  int32_t ld;        /* elements between consecutive pixels/rows of src (its channel count) */
+  int32_t c_off;     /* first channel of the segment                                        */
+  int32_t C;         /* channels in the segment; multiple of 64                             */
+  int32_t dy, dx;    /* spatial tap offset in (upsampled) input coordinates                 */
+  int32_t dt;        /* temporal tap offset in frames (mode 2)                              */
+} hi3d_seg;
+
+enum { HI3D_ROWS_PLAIN = 0, HI3D_ROWS_CONV2D = 1, HI3D_ROWS_TEMPORAL = 2 };
+enum { HI3D_ACT_NONE = 0, HI3D_ACT_SILU = 1, HI3D_ACT_GEGLU = 2 };
+
+typedef struct {
+  int32_t M, N, K;          /* K == sum of seg[i].C; N multiple of 8                                   */
+  int32_t mode;             /* HI3D_ROWS_*                                                             */
+  int32_t Ho, Wo;           /* CONV2D: output H, W (M == Nimg*Ho*Wo).  TEMPORAL: Ho*Wo = rows per frame */
+  int32_t Hs, Ws;           /* CONV2D: source H, W (before the optional x2 nearest upsample)           */
+  int32_t stride;           /* CONV2D: 1 or 2                                                          */
+  int32_t ups;              /* CONV2D: 1 -> taps address the x2 nearest-upsampled source               */
+  int32_t T;                /* TEMPORAL: frames per clip                                               */
+  int32_t nseg;
+  hi3d_seg seg[HI3D_MAX_SEGS];
+  const void* W;            /* fp16 [N, K], K contiguous, K ordered as the segments                    */
+  const float* bias;        /* [N] or NULL                                                             */
+  const void* rowbias;      /* fp16 [R, rb_ld] or NULL; row r = (m / rb_div) % rb_mod                  */
+  int32_t rb_div, rb_mod, rb_ld;
+  int32_t act;              /* HI3D_ACT_*; GEGLU: W rows interleaved (value, gate), output width N/2   */
+  const void* residual;     /* fp16 [M, res_ld] or NULL, added after the activation                    */
+  int32_t res_ld;
+  const void* blend_x;      /* fp16 [M, blend_ld] or NULL: out = alpha*blend_x + (1-alpha)*value       */
+  int32_t blend_ld;
+  float alpha;
+  void* out;                /* fp16 [M, out_ld]                                                        */
+  int32_t out_ld;
+} hi3d_gemm_params;
+
+int hi3d_gemm(const hi3d_gemm_params* p, void* stream);
+/* same contract, tcgen05/TMEM engine (UTCHMMA); selected by the host when validated on the device */
+int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream);
+
+/* Tiny channel counts (UNet input 8|17 ch, VAE image 3 ch / latent 4 ch) are zero-padded to 64 channels by
+ * hi3d_sampler_pre / hi3d_nchw_to_nhwc so that the same engine serves input_blocks.0.0 (video_model.py:186-191),
+ * encoder.conv_in (model.py:517) and decoder.conv_in (model.py:654); tiny C_out (4 | 8 | 3) is padded to 8. */
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation
+ * --------------------------------------------------------------------------------------------- */
+/* GroupNorm(32 groups) [+ SiLU] over `rows_per_sample` consecutive rows x (C/32) channels, on the virtual
+ * channel-concat of up to two NHWC fp16 sources (x1: C1 channels, x2: C2 channels or NULL).
+ * Replaces GroupNorm32 (util.py:274-276; eps 1e-5; temporal ResBlock: rows_per_sample = T*H*W, i.e. the
+ * reduction over (C/32, T, H, W) of video_model.py:71-76), Normalize (attention.py:125-128, model.py:52-55;
+ * eps 1e-6) and the following nn.SiLU / x*sigmoid(x).  Two launches: partial sums then apply.
+ * ws: fp32 workspace of hi3d_groupnorm_ws_floats(n_samples) floats. Output y: fp16 [rows, C1+C2]. */
+int64_t hi3d_groupnorm_ws_floats(int n_samples);
+int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
+                        const float* gamma, const float* beta, float eps, int apply_silu, void* y, float* ws,
+                        void* stream);
+
+/* LayerNorm over the last dim C (<= 2560, multiple of 8) of [M, C] fp16 (+ optional broadcast add before the norm:
+ * x + addvec[((m / add_div) % add_mod), :], the `x_mix = x + emb` of video_attention.py:286-287).
+ * Replaces nn.LayerNorm at attention.py:520-522, video_attention.py:51,79,93-94.  y fp16 [M, C]. */
+int hi3d_layernorm(const void* x, const void* addvec, int add_div, int add_mod, int64_t M, int C, const float* gamma,
+                   const float* beta, float eps, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention
+ * --------------------------------------------------------------------------------------------- */
+/* Spatial self-attention core, head dim 64: softmax(Q K^T * scale) V per (image, head).
+ * qkv: fp16 [n_img*L, 3*C] with q | k | v column blocks, heads contiguous (C = heads*64); out fp16 [n_img*L, C].
+ * Replaces F.scaled_dot_product_attention / xformers.memory_efficient_attention at attention.py:334,427-439. */
+int hi3d_attention_d64(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream);
+
+/* Temporal self-attention core over the frame axis (T <= 16), head dim 64, for every (clip, pixel, head):
+ * token row of (b, t, s) is (b*T + t)*S + s -- the "(b t) s c -> (b s) t c" rearrange of
+ * video_attention.py:114,137-139 is done by addressing, never materialised.
+ * qkv fp16 [B*T*S, 3*C]; out fp16 [B*T*S, C].  Replaces attn1 core at video_attention.py:125. */
+int hi3d_temporal_attention_d64(const void* qkv, int B, int T, int S, int heads, float scale, void* out,
+                                void* stream);
+
+/* Row softmax in place on fp16 [rows, L] (scores * scale), and 2-D transpose [R, Cc] -> [Cc, R] (fp16):
+ * building blocks of the VAE single-head d=512 attention (model.py:180-195) on top of hi3d_gemm. */
+int hi3d_softmax_rows(void* s, int64_t rows, int L, float scale, void* stream);
+int hi3d_transpose(const void* in, int R, int Cc, int in_ld, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sampler-side fused elementwise kernels (EulerEDMSampler / Denoiser / LinearPredictionGuider)
+ * --------------------------------------------------------------------------------------------- */
+/* timestep_embedding (util.py:207-231): t fp32 [n] -> fp16 [n, dim] = [cos | sin]. */
+int hi3d_timestep_embedding(const float* t, int n, int dim, float max_period, void* out, void* stream);
+
+/* Build the UNet input for one CFG-batched step: prepare_inputs (guiders.py:88-99) + Denoiser c_in scaling
+ * (denoiser.py:33-37) + OpenAIWrapper concat (wrappers.py:27) + NCHW->NHWC fp16.
+ * x fp32 NCHW [F, Cx, H, W]; sigma fp32 [F]; concat_uc / concat_c fp16-or-fp32 NCHW [F, Cc, H, W] (concat_uc may be
+ * NULL == zeros); out fp16 NHWC [2F, H, W, Cpad] (channels [x*c_in | concat | 0-pad]); first F samples = uc half. */
+int hi3d_sampler_pre(const float* x, const float* sigma, const void* concat_uc, const void* concat_c,
+                     int concat_is_fp32, int F, int Cx, int Cc, int H, int W, int Cpad, void* out, void* stream);
+
+/* Finish the step: denoised = net*c_out + x*c_skip per half (denoiser.py:36-39), CFG combine with the per-frame
+ * scale (guiders.py:78-86), d = (x - denoised)/sigma and Euler update x += d*(sigma_next - sigma)
+ * (sampling.py:99-103, sampling_utils.py:34).  net fp16 NHWC [2F, H, W, net_ld] (first Cx channels used);
+ * x fp32 NCHW [F, Cx, H, W] updated in place (x_out may alias x); scale fp32 [T] (frame t = f % T);
+ * denoised_out optional fp32 NCHW [F, Cx, H, W] (the guided D(x, sigma), for teacher-forced parity checks). */
+int hi3d_sampler_post(const void* net, int net_ld, const float* x, const float* sigma, const float* sigma_next,
+                      const float* scale, int T, int F, int Cx, int H, int W, float* x_out, float* denoised_out,
+                      void* stream);
+
+/* Stage-2 re-noise blend (pipeline_i2v_eval_v02.py:131-132): lat = lat*(1-a) + (init*sigma + z)*a, fp32. */
+int hi3d_renoise_blend(float* lat, const float* init, const float* z, float alpha, float sigma, int64_t n,
+                       void* stream);
+
+/* Layout / dtype helpers: NCHW (fp32 or fp16) -> NHWC fp16 with channel padding, and NHWC fp16 -> NCHW fp32/fp16
+ * (first C channels), used at the VAE / latent boundaries (autoencoder.py:468-505, diffusion.py:117-150). */
+int hi3d_nchw_to_nhwc(const void* in, int in_is_fp32, int N, int C, int H, int W, int Cpad, float scale, void* out,
+                      void* stream);
+int hi3d_nhwc_to_nchw(const void* in, int in_ld, int N, int C, int H, int W, float scale, void* out, int out_is_fp32,
+                      void* stream);
+
+/* DiagonalGaussianDistribution.sample / mode (distributions.py:24-41,71) * scale_factor (diffusion.py:149):
+ * moments fp16 NHWC [N, H, W, ld] (mean = ch 0..C-1, logvar = ch C..2C-1), noise fp32 NCHW or NULL (mode),
+ * out fp32 NCHW [N, C, H, W]. */
+int hi3d_gaussian_sample(const void* moments, int ld, const float* noise, int N, int C, int H, int W, float scale,
+                         float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HI3D_B200_H_ */
