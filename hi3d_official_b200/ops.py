@@ -93,9 +93,11 @@ class Gemm:
             if bias.numel() != Nn:
                 raise ValueError("bias size")
         p.bias = _ptr(bias)
-        if rowbias is not None:
-            _chk16(rowbias, "rowbias")
-            p.rb_ld = rowbias.shape[-1]
+        if rowbias is not None:     # may be a column slice of a wider matrix (rows of stride rb_ld)
+            if rowbias.dtype != F16 or not rowbias.is_cuda or rowbias.dim() != 2 or rowbias.stride(1) != 1 \
+                    or rowbias.shape[1] < Nn:
+                raise ValueError("rowbias: expected CUDA fp16 [R, >=N] with unit column stride")
+            p.rb_ld = rowbias.stride(0)
         p.rowbias, p.rb_div, p.rb_mod = _ptr(rowbias), rb_div, rb_mod
         p.act = act
         n_out = Nn // 2 if act == ACT_GEGLU else Nn

@@ -1,0 +1,546 @@
+"""VideoUNet: drop-in for `sgm.modules.diffusionmodules.video_model.VideoUNet` (video_model.py:84-501).
+
+Same constructor kwargs, same `state_dict` keys/shapes, same `forward` signature and output -- but the
+module is a parameter container plus a *compiled launch plan*: for a given (batch, H, W, T) the whole forward
+is a flat list of C-ABI kernel launches (hi3d_gemm / hi3d_groupnorm_silu / hi3d_layernorm /
+hi3d_attention_d64 / hi3d_temporal_attention_d64 ...) over pre-allocated channels-last fp16 buffers with
+pre-baked parameter blocks, replayable under a CUDA graph.  There is no per-op nn.Module graph and no
+PyTorch compute on the path.
+
+Algebraic folds relative to the reference graph (all exact in real arithmetic):
+  * single-token cross-attention attn2(x, ctx) == to_out(to_v(ctx)) -> a per-sample bias row added in the
+    epilogue of the attn1 output projection (to_q / to_k / norm2 are dead compute);
+  * time_pos_embed(arange(T)) depends only on T -> computed once per plan;
+  * label_emb(y) and the cross-attention rows are step-invariant -> `prepare_conditioning` runs them once
+    per video; the generic `forward()` recomputes them every call (it cannot know the caller's loop);
+  * 1x1 skip convs are extra K-segments of the second 3x3 conv GEMM; th.cat([h, hs.pop()]) is never
+    materialised (two K-segments per tap); AlphaBlender and every residual add live in GEMM epilogues;
+  * "(b t) s c <-> (b s) t c" rearranges of the temporal transformer are pure addressing.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops, pack
+from .spec import Layer, UNetConfig, unet_param_shapes, unet_plan
+
+F16 = torch.float16
+CIN_PAD = 64     # UNet input channels are zero-padded to one 64-wide K segment per tap
+COUT_PAD = 8     # final conv output channels padded to the engine's N granularity
+
+
+class _ParamTree(nn.Module):
+    """Nested holder so parameters get the reference's dotted names (input_blocks.1.0.in_layers.2.weight ...)."""
+
+    def put(self, dotted: str, p: nn.Parameter):
+        parts = dotted.split(".")
+        node = self
+        for q in parts[:-1]:
+            if q not in node._modules:
+                node.add_module(q, _ParamTree())
+            node = node._modules[q]
+        node.register_parameter(parts[-1], p)
+
+
+class Arena:
+    """Named scratch buffers: one allocation per tag, sized to the largest request, handed out as views."""
+
+    def __init__(self, device):
+        self.device = device
+        self.req: Dict[str, int] = {}
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.views: List[Tuple[str, int, int, list]] = []
+
+    def want(self, tag: str, rows: int, cols: int) -> "LazyBuf":
+        n = rows * cols
+        self.req[tag] = max(self.req.get(tag, 0), n)
+        return LazyBuf(self, tag, rows, cols)
+
+    def materialise(self):
+        for tag, n in self.req.items():
+            if tag not in self.bufs or self.bufs[tag].numel() < n:
+                self.bufs[tag] = torch.zeros(n, dtype=F16, device=self.device)
+
+    def get(self, tag: str, rows: int, cols: int) -> torch.Tensor:
+        return self.bufs[tag][: rows * cols].view(rows, cols)
+
+    def nbytes(self) -> int:
+        return sum(b.numel() * 2 for b in self.bufs.values())
+
+
+class LazyBuf:
+    __slots__ = ("arena", "tag", "rows", "cols")
+
+    def __init__(self, arena, tag, rows, cols):
+        self.arena, self.tag, self.rows, self.cols = arena, tag, rows, cols
+
+    @property
+    def t(self) -> torch.Tensor:
+        return self.arena.get(self.tag, self.rows, self.cols)
+
+
+class VideoUNet(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.cfg = UNetConfig.from_kwargs(**kwargs)
+        self.plan_desc = unet_plan(self.cfg)
+        self.in_channels, self.out_channels = self.cfg.in_channels, self.cfg.out_channels
+        self.model_channels, self.num_classes = self.cfg.model_channels, self.cfg.num_classes
+        tree = _ParamTree()
+        for name, shp in unet_param_shapes(self.cfg).items():
+            tree.put(name, nn.Parameter(torch.empty(shp), requires_grad=False))
+        # expose the reference's top-level attribute names (time_embed, label_emb, input_blocks, ...)
+        for k, m in tree._modules.items():
+            self.add_module(k, m)
+        self._packed: Optional[dict] = None
+        self._plans: Dict[tuple, "_Plan"] = {}
+        self.engine = "mma"
+
+    # ---- parameter lifecycle ---------------------------------------------------------------------------
+    def _invalidate(self):
+        self._packed = None
+        self._plans = {}
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._invalidate()
+        return super().load_state_dict(*a, **k)
+
+    def set_engine(self, engine: str):
+        if engine not in ("mma", "tc5"):
+            raise ValueError(engine)
+        if engine != self.engine:
+            self.engine = engine
+            self._plans = {}
+
+    @property
+    def device(self):
+        return self.out._modules["0"].weight.device
+
+    # ---- weight packing ----------------------------------------------------------------------------------
+    def _pack(self) -> dict:
+        if self._packed is not None:
+            return self._packed
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("hi3d_official_b200.VideoUNet computes only on CUDA (B200); call .cuda() first -- "
+                               "there is no CPU fallback")
+        P: dict = {}
+        lin, bias = pack.pack_linear, pack.pack_bias
+
+        def f32(k):
+            return sd[k].float().contiguous()
+
+        def pb(k):
+            return sd[k].float().contiguous()
+        mc = self.cfg.model_channels
+        P["time_embed.0"] = (lin(sd["time_embed.0.weight"]), pb("time_embed.0.bias"))
+        P["time_embed.2"] = (lin(sd["time_embed.2.weight"]), pb("time_embed.2.bias"))
+        P["label_emb.0"] = (lin(sd["label_emb.0.0.weight"]), pb("label_emb.0.0.bias"))
+        P["label_emb.2"] = (lin(sd["label_emb.0.2.weight"]), pb("label_emb.0.2.bias"))
+        emb_w, emb_b, emb_off, off = [], [], {}, 0
+        layers = [L for blk in self.plan_desc.input_blocks + [self.plan_desc.middle] + self.plan_desc.output_blocks
+                  for L in blk]
+        for L in layers:
+            n = L.name
+            if L.kind == "conv_in":
+                P[n] = (pack.pack_conv2d(sd[n + "weight"], cin_pad=CIN_PAD), pb(n + "bias"))
+            elif L.kind == "down":
+                P[n] = (pack.pack_conv2d(sd[n + "op.weight"]), pb(n + "op.bias"))
+            elif L.kind == "up":
+                P[n] = (pack.pack_conv2d(sd[n + "conv.weight"]), pb(n + "conv.bias"))
+            elif L.kind == "res":
+                for sub, tconv in (("", False), ("time_stack.", True)):
+                    q = n + sub
+                    pk = pack.pack_conv3d_t if tconv else pack.pack_conv2d
+                    P[q + "gn1"] = (f32(q + "in_layers.0.weight"), f32(q + "in_layers.0.bias"))
+                    P[q + "conv1"] = (pk(sd[q + "in_layers.2.weight"]), pb(q + "in_layers.2.bias"))
+                    P[q + "gn2"] = (f32(q + "out_layers.0.weight"), f32(q + "out_layers.0.bias"))
+                    w2, b2 = pk(sd[q + "out_layers.3.weight"]), pb(q + "out_layers.3.bias")
+                    if q + "skip_connection.weight" in sd:
+                        w2 = pack.cat_k(w2, pack.pack_conv2d(sd[q + "skip_connection.weight"]))
+                        b2 = b2 + pb(q + "skip_connection.bias")
+                    P[q + "conv2"] = (w2, b2.contiguous())
+                    emb_w.append(lin(sd[q + "emb_layers.1.weight"]))
+                    emb_b.append(pb(q + "emb_layers.1.bias"))
+                    emb_off[q] = (off, emb_w[-1].shape[0])
+                    off += emb_w[-1].shape[0]
+                P[n + "alpha"] = float(torch.sigmoid(sd[n + "time_mixer.mix_factor"].float()).item())
+            elif L.kind == "attn":
+                P[n + "norm"] = (f32(n + "norm.weight"), f32(n + "norm.bias"))
+                P[n + "proj_in"] = (lin(sd[n + "proj_in.weight"]), pb(n + "proj_in.bias"))
+                P[n + "proj_out"] = (lin(sd[n + "proj_out.weight"]), pb(n + "proj_out.bias"))
+                P[n + "tpe0"] = (lin(sd[n + "time_pos_embed.0.weight"]), pb(n + "time_pos_embed.0.bias"))
+                P[n + "tpe2"] = (lin(sd[n + "time_pos_embed.2.weight"]), pb(n + "time_pos_embed.2.bias"))
+                P[n + "alpha"] = float(torch.sigmoid(sd[n + "time_mixer.mix_factor"].float()).item())
+                for d in range(self.cfg.transformer_depth):
+                    for q, temporal in ((n + f"transformer_blocks.{d}.", False), (n + f"time_stack.{d}.", True)):
+                        for nm in ("norm1", "norm3") + (("norm_in",) if temporal else ()):
+                            P[q + nm] = (f32(q + nm + ".weight"), f32(q + nm + ".bias"))
+                        P[q + "qkv"] = torch.cat([lin(sd[q + "attn1.to_q.weight"]), lin(sd[q + "attn1.to_k.weight"]),
+                                                  lin(sd[q + "attn1.to_v.weight"])], 0).contiguous()
+                        P[q + "to_out"] = (lin(sd[q + "attn1.to_out.0.weight"]), pb(q + "attn1.to_out.0.bias"))
+                        P[q + "ca_v"] = lin(sd[q + "attn2.to_v.weight"])
+                        P[q + "ca_out"] = (lin(sd[q + "attn2.to_out.0.weight"]), pb(q + "attn2.to_out.0.bias"))
+                        for ff in ("ff",) + (("ff_in",) if temporal else ()):
+                            P[q + ff + "1"] = pack.pack_geglu(sd[q + ff + ".net.0.proj.weight"],
+                                                              sd[q + ff + ".net.0.proj.bias"])
+                            P[q + ff + "2"] = (lin(sd[q + ff + ".net.2.weight"]), pb(q + ff + ".net.2.bias"))
+        P["emb_all"] = (torch.cat(emb_w, 0).contiguous(), torch.cat(emb_b, 0).contiguous())
+        P["emb_off"], P["emb_total"] = emb_off, off
+        P["out.gn"] = (f32("out.0.weight"), f32("out.0.bias"))
+        P["out.conv"] = (pack.pack_conv2d(sd["out.2.weight"], cout_pad=COUT_PAD),
+                         pack.pack_bias(sd["out.2.bias"], self.cfg.out_channels, COUT_PAD))
+        self._packed = P
+        return P
+
+    # ---- plans --------------------------------------------------------------------------------------------
+    def get_plan(self, N: int, H: int, W: int, T: int) -> "_Plan":
+        key = (N, H, W, T, self.engine)
+        if key not in self._plans:
+            self._plans[key] = _Plan(self, N, H, W, T)
+        return self._plans[key]
+
+    # ---- reference-compatible forward ------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor, context: Optional[torch.Tensor] = None,
+                y: Optional[torch.Tensor] = None, time_context: Optional[torch.Tensor] = None,
+                num_video_frames: Optional[int] = None, image_only_indicator: Optional[torch.Tensor] = None):
+        assert (y is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        assert context is not None and num_video_frames is not None
+        if time_context is not None:
+            raise NotImplementedError("explicit time_context: Hi3D configs use use_spatial_context=True")
+        if image_only_indicator is not None and bool(image_only_indicator.any()):
+            raise NotImplementedError("image_only_indicator != 0 (image-only frames) is outside the Hi3D hot path")
+        N, Cin, H, W = x.shape
+        assert Cin == self.in_channels, f"expected {self.in_channels} input channels, got {Cin}"
+        plan = self.get_plan(N, H, W, num_video_frames)
+        plan.prepare_conditioning(context, y)
+        ops.nchw_to_nhwc(x.contiguous(), plan.xin.t.view(N, H, W, CIN_PAD))
+        plan.set_timesteps(timesteps)
+        plan.run()
+        out = torch.empty(N, self.out_channels, H, W, dtype=F16, device=x.device)
+        ops.nhwc_to_nchw(plan.net_out.t, out)
+        return out
+
+
+# ==================================================================================================================
+class _Plan:
+    """Flat launch list for one (N, H, W, T): buffers, pre-baked GEMM parameter blocks, per-step entry points."""
+
+    def __init__(self, net: VideoUNet, N: int, H: int, W: int, T: int):
+        if N % T:
+            raise ValueError(f"batch {N} is not a multiple of num_video_frames {T}")
+        if T > 16:
+            raise NotImplementedError("temporal attention kernel supports T <= 16 frames")
+        nlev = len(net.cfg.channel_mult)
+        if H % (1 << (nlev - 1)) or W % (1 << (nlev - 1)):
+            raise ValueError(f"H, W = {H}, {W} must be divisible by {1 << (nlev - 1)}")
+        self.net, self.N, self.H, self.W, self.T, self.B = net, N, H, W, T, N // T
+        self.P = net._pack()
+        self.dev = net.device
+        self.engine = net.engine
+        self.arena = Arena(self.dev)
+        self.steps: List = []          # main per-step launch list (built lazily as (kind, builder) then baked)
+        self._build: List = []         # deferred builders, run after the arena is materialised
+        self._cond_build: List = []
+        self.cond_steps: List = []
+        self.flops = 0.0
+        self._graph = None
+        cfg = net.cfg
+        mc, E = cfg.model_channels, cfg.model_channels * 4
+        dev = self.dev
+        # small persistent (non-arena) tensors
+        self.t_in = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.temb = torch.zeros(N, mc, dtype=F16, device=dev)
+        self.e1 = torch.zeros(N, E, dtype=F16, device=dev)
+        self.emb_act = torch.zeros(N, E, dtype=F16, device=dev)
+        self.emb_all = torch.zeros(N, self.P["emb_total"], dtype=F16, device=dev)
+        self.label = torch.zeros(N, E, dtype=F16, device=dev)
+        self.y_in = torch.zeros(N, cfg.adm_in_channels, dtype=F16, device=dev)
+        self.y_h = torch.zeros(N, E, dtype=F16, device=dev)
+        self.ctx_in = torch.zeros(N, cfg.context_dim, dtype=F16, device=dev)
+        self.ctx_first = torch.zeros(self.B, cfg.context_dim, dtype=F16, device=dev)
+        self.gn_ws = ops.groupnorm_ws(N, dev)
+        self.frame_idx = torch.arange(T, dtype=torch.float32, device=dev)
+        self._cond_key = None
+        self._compile()
+
+    # ---- helpers -----------------------------------------------------------------------------------------------
+    def _gemm(self, lst, segs_fn, W, out: LazyBuf, M, **kw):
+        """Defer Gemm construction until buffers exist. segs_fn() -> list[SegSpec]; tensor kwargs may be LazyBuf."""
+        def build():
+            k2 = {}
+            for k, v in kw.items():
+                k2[k] = v.t if isinstance(v, LazyBuf) else v
+            g = ops.Gemm(segs_fn(), W, out.t if isinstance(out, LazyBuf) else out, M, engine=self.engine, **k2)
+            self.flops += g.flops if lst is self._build else 0.0
+            return g
+        lst.append(build)
+
+    def _call(self, lst, fn):
+        lst.append(lambda: fn)
+
+    def _compile(self):
+        net, P, cfg = self.net, self.P, self.net.cfg
+        N, T, B = self.N, self.T, self.B
+        A = self.arena
+        H, W = self.H, self.W
+        mc, E = cfg.model_channels, cfg.model_channels * 4
+        bl = self._build
+
+        # ---------------- per-step embedding path (video_model.py:456-469, openaimodel.py:341) ----------------
+        self._call(bl, lambda: ops.timestep_embedding(self.t_in, mc, self.temb))
+        self._gemm(bl, lambda: [ops.SegSpec(self.temb)], P["time_embed.0"][0], self.e1, N, bias=P["time_embed.0"][1],
+                   act=ops.ACT_SILU)
+        self._gemm(bl, lambda: [ops.SegSpec(self.e1)], P["time_embed.2"][0], self.emb_act, N,
+                   bias=P["time_embed.2"][1], rowbias=self.label, rb_div=1, rb_mod=N, act=ops.ACT_SILU)
+        self._gemm(bl, lambda: [ops.SegSpec(self.emb_act)], P["emb_all"][0], self.emb_all, N, bias=P["emb_all"][1])
+
+        # ---------------- conditioning path (once per video) ----------------
+        cl = self._cond_build
+        self._gemm(cl, lambda: [ops.SegSpec(self.y_in)], P["label_emb.0"][0], self.y_h, N, bias=P["label_emb.0"][1],
+                   act=ops.ACT_SILU)
+        self._gemm(cl, lambda: [ops.SegSpec(self.y_h)], P["label_emb.2"][0], self.label, N, bias=P["label_emb.2"][1])
+
+        # ---------------- main body ----------------
+        self.xin = A.want("xin", N * H * W, CIN_PAD)
+        hs: List[Tuple[LazyBuf, int, int, int]] = []          # (buffer, C, h, w)
+        cur: Tuple[LazyBuf, int, int, int] = None
+        self._pp = 0
+
+        def next_out(rows, C, persist_tag=None):
+            if persist_tag:
+                return A.want(persist_tag, rows, C)
+            self._pp ^= 1
+            return A.want(f"blk{self._pp}", rows, C)
+
+        h, w = H, W
+        for bi, blk in enumerate(self.plan_desc_blocks("input")):
+            for li, L in enumerate(blk):
+                last = li == len(blk) - 1
+                tag = f"hs{bi}" if last else None
+                if L.kind == "conv_in":
+                    out = next_out(N * h * w, L.cout, tag)
+                    self._conv(bl, [self.xin], P[L.name], out, h, w, h, w)
+                    cur = (out, L.cout, h, w)
+                elif L.kind == "res":
+                    out = next_out(N * h * w, L.cout, tag)
+                    self._resblock(L, [cur[0]], [cur[1]], out, h, w)
+                    cur = (out, L.cout, h, w)
+                elif L.kind == "attn":
+                    out = next_out(N * h * w, L.cout, tag)
+                    self._transformer(L, cur[0], out, h, w)
+                    cur = (out, L.cout, h, w)
+                elif L.kind == "down":
+                    out = next_out(N * (h // 2) * (w // 2), L.cout, tag)
+                    self._conv(bl, [cur[0]], P[L.name], out, h // 2, w // 2, h, w, stride=2)
+                    h, w = h // 2, w // 2
+                    cur = (out, L.cout, h, w)
+            hs.append(cur)
+        for L in self.net.plan_desc.middle:
+            out = next_out(N * h * w, L.cout)
+            if L.kind == "res":
+                self._resblock(L, [cur[0]], [cur[1]], out, h, w)
+            else:
+                self._transformer(L, cur[0], out, h, w)
+            cur = (out, L.cout, h, w)
+        for blk in self.plan_desc_blocks("output"):
+            skip = hs.pop()
+            assert (skip[2], skip[3]) == (h, w)
+            srcs, cs = [cur[0], skip[0]], [cur[1], skip[1]]
+            for L in blk:
+                if L.kind == "res":
+                    out = next_out(N * h * w, L.cout)
+                    self._resblock(L, srcs, cs, out, h, w)
+                    cur = (out, L.cout, h, w)
+                elif L.kind == "attn":
+                    out = next_out(N * h * w, L.cout)
+                    self._transformer(L, cur[0], out, h, w)
+                    cur = (out, L.cout, h, w)
+                elif L.kind == "up":
+                    out = next_out(N * 4 * h * w, L.cout)
+                    self._conv(bl, [cur[0]], P[L.name], out, 2 * h, 2 * w, h, w, ups=1)
+                    h, w = 2 * h, 2 * w
+                    cur = (out, L.cout, h, w)
+        # out: GN32 -> SiLU -> conv3x3 (video_model.py:436-440,500-501)
+        M = N * h * w
+        g = A.want("gn", M, cur[1])
+        gam, bet = P["out.gn"]
+        src = cur[0]
+        self._call(bl, lambda: ops.groupnorm_silu(src.t, None, N, h * w, gam, bet, 1e-5, True, g.t, self.gn_ws))
+        self.net_out = A.want("net_out", M, COUT_PAD)
+        self._conv(bl, [g], P["out.conv"], self.net_out, h, w, h, w)
+
+        # ---------------- materialise buffers, bake launches ----------------
+        A.materialise()
+        self.steps = [b() for b in self._build]
+        self.cond_steps = [b() for b in self._cond_build]
+        self._build = self._cond_build = None
+
+    def plan_desc_blocks(self, which):
+        return self.net.plan_desc.input_blocks if which == "input" else self.net.plan_desc.output_blocks
+
+    # ---- layer emitters ----------------------------------------------------------------------------------------
+    def _conv(self, lst, srcs: List[LazyBuf], wb, out: LazyBuf, ho, wo, hs_, ws_, stride=1, ups=0, **kw):
+        Wt, b = wb
+        M = self.N * ho * wo
+        self._gemm(lst, lambda: ops.conv_taps([s.t for s in srcs]), Wt, out, M, mode=ops.ROWS_CONV2D,
+                   geom=dict(Ho=ho, Wo=wo, Hs=hs_, Ws=ws_, stride=stride, ups=ups), bias=b, **kw)
+
+    def _emb_slice(self, q):
+        off, n = self.P["emb_off"][q]
+        return self.emb_all[:, off:off + n]
+
+    def _resblock(self, L: Layer, srcs: List[LazyBuf], cs: List[int], out: LazyBuf, h: int, w: int):
+        """VideoResBlock (video_model.py:62-81) = spatial ResBlock (openaimodel.py:328-354) + temporal ResBlock
+        (dims=3, kernel (3,1,1), GroupNorm over (C/32, T, H, W)) + AlphaBlender, as 4 GN launches + 4 GEMMs."""
+        P, A, bl, N, T, B = self.P, self.arena, self._build, self.N, self.T, self.B
+        n = L.name
+        HW = h * w
+        M = N * HW
+        cin, cout = sum(cs), L.cout
+        x1 = srcs[0]
+        x2 = srcs[1] if len(srcs) > 1 else None
+        g_in = A.want("gn", M, cin)
+        hbuf = A.want("h", M, cout)
+        g_mid = A.want("gn", M, cout)
+        xs = A.want("xs", M, cout)
+        ws = self.gn_ws
+        # -- spatial half
+        gam, bet = P[n + "gn1"]
+        self._call(bl, lambda: ops.groupnorm_silu(x1.t, x2.t if x2 else None, N, HW, gam, bet, 1e-5, True, g_in.t, ws))
+        emb1 = self._emb_slice(n)
+        self._gemm(bl, lambda: ops.conv_taps([g_in.t]), P[n + "conv1"][0], hbuf, M, mode=ops.ROWS_CONV2D,
+                   geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv1"][1], rowbias=emb1, rb_div=HW, rb_mod=N)
+        gam2, bet2 = P[n + "gn2"]
+        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, N, HW, gam2, bet2, 1e-5, True, g_mid.t, ws))
+        if cin != cout:
+            self._gemm(bl, lambda: ops.conv_taps([g_mid.t]) + [ops.SegSpec(s.t) for s in srcs], P[n + "conv2"][0], xs, M,
+                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1])
+        else:
+            assert x2 is None
+            self._gemm(bl, lambda: ops.conv_taps([g_mid.t]), P[n + "conv2"][0], xs, M, mode=ops.ROWS_CONV2D,
+                       geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1], residual=x1)
+        # -- temporal half: statistics over (T, H, W) per clip, 3-tap conv along frames
+        q = n + "time_stack."
+        g3, b3 = P[q + "gn1"]
+        self._call(bl, lambda: ops.groupnorm_silu(xs.t, None, B, T * HW, g3, b3, 1e-5, True, g_mid.t, ws))
+        geo = dict(Ho=HW, Wo=1, T=T)
+        emb2 = self._emb_slice(q)
+        self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv1"][0], hbuf, M, mode=ops.ROWS_TEMPORAL, geom=geo,
+                   bias=P[q + "conv1"][1], rowbias=emb2, rb_div=HW, rb_mod=N)
+        g4, b4 = P[q + "gn2"]
+        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, B, T * HW, g4, b4, 1e-5, True, g_mid.t, ws))
+        # x_t = xs + conv(...);  out = alpha*xs + (1-alpha)*x_t   (util.py:358-369)
+        self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv2"][0], out, M, mode=ops.ROWS_TEMPORAL, geom=geo,
+                   bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"])
+
+    def _transformer(self, L: Layer, x: LazyBuf, out: LazyBuf, h: int, w: int):
+        """SpatialVideoTransformer.forward (video_attention.py:230-301), see module docstring for the folds."""
+        P, A, bl, cl, N, T, B = self.P, self.arena, self._build, self._cond_build, self.N, self.T, self.B
+        n, C = L.name, L.cin
+        HW = h * w
+        M = N * HW
+        heads = C // self.net.cfg.num_head_channels
+        if self.net.cfg.num_head_channels != 64:
+            raise NotImplementedError("attention kernels are specialised for head dim 64")
+        dev = self.dev
+        gn, t0, t1, t2 = A.want("gn", M, C), A.want("t0", M, C), A.want("t1", M, C), A.want("t2", M, C)
+        ln, qkv, att, ffh = A.want("ln", M, C), A.want("qkv", M, 3 * C), A.want("att", M, C), A.want("ffh", M, 4 * C)
+        ws = self.gn_ws
+        # time_pos_embed(timestep_embedding(arange(T))) : plan constant (video_attention.py:266-276)
+        tpe_in = torch.zeros(T, C, dtype=F16, device=dev)
+        tpe_h = torch.zeros(T, 4 * C, dtype=F16, device=dev)
+        emb_t = torch.zeros(T, C, dtype=F16, device=dev)
+        ops.timestep_embedding(self.frame_idx, C, tpe_in, float(self.net.cfg.max_ddpm_temb_period))
+        ops.Gemm([ops.SegSpec(tpe_in)], P[n + "tpe0"][0], tpe_h, T, bias=P[n + "tpe0"][1], act=ops.ACT_SILU)()
+        ops.Gemm([ops.SegSpec(tpe_h)], P[n + "tpe2"][0], emb_t, T, bias=P[n + "tpe2"][1])()
+
+        gam, bet = P[n + "norm"]
+        self._call(bl, lambda: ops.groupnorm_silu(x.t, None, N, HW, gam, bet, 1e-6, False, gn.t, ws))
+        self._gemm(bl, lambda: [ops.SegSpec(gn.t)], P[n + "proj_in"][0], t0, M, bias=P[n + "proj_in"][1])
+        tok = t0
+        for d in range(self.net.cfg.transformer_depth):
+            qs, qt = n + f"transformer_blocks.{d}.", n + f"time_stack.{d}."
+            # step-invariant single-token cross-attention rows: to_out(to_v(ctx)) + bias
+            v_s = torch.zeros(N, C, dtype=F16, device=dev); r_s = torch.zeros(N, C, dtype=F16, device=dev)
+            v_t = torch.zeros(B, C, dtype=F16, device=dev); r_t = torch.zeros(B, C, dtype=F16, device=dev)
+            self._gemm(cl, lambda: [ops.SegSpec(self.ctx_in)], P[qs + "ca_v"], v_s, N)
+            self._gemm(cl, lambda v_s=v_s: [ops.SegSpec(v_s)], P[qs + "ca_out"][0], r_s, N, bias=P[qs + "ca_out"][1])
+            self._gemm(cl, lambda: [ops.SegSpec(self.ctx_first)], P[qt + "ca_v"], v_t, B)
+            self._gemm(cl, lambda v_t=v_t: [ops.SegSpec(v_t)], P[qt + "ca_out"][0], r_t, B, bias=P[qt + "ca_out"][1])
+            # ---- spatial BasicTransformerBlock (attention.py:551-572)
+            self._ln(bl, tok, P[qs + "norm1"], ln, M)
+            self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qs + "qkv"], qkv, M)
+            self._call(bl, lambda: ops.attention_d64(qkv.t, N, HW, heads, att.t))
+            self.flops += 4.0 * N * HW * HW * C
+            self._gemm(bl, lambda: [ops.SegSpec(att.t)], P[qs + "to_out"][0], t1, M, bias=P[qs + "to_out"][1],
+                       residual=tok, rowbias=r_s, rb_div=HW, rb_mod=N)
+            self._ln(bl, t1, P[qs + "norm3"], ln, M)
+            self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qs + "ff1"][0], ffh, M, bias=P[qs + "ff1"][1], act=ops.ACT_GEGLU)
+            self._gemm(bl, lambda: [ops.SegSpec(ffh.t)], P[qs + "ff2"][0], t2, M, bias=P[qs + "ff2"][1], residual=t1)
+            # ---- temporal VideoTransformerBlock on x_mix = t2 + emb_t (video_attention.py:109-140, :286-289)
+            self._ln(bl, t2, P[qt + "norm_in"], ln, M, addvec=emb_t, add_div=HW, add_mod=T)
+            self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qt + "ff_in1"][0], ffh, M, bias=P[qt + "ff_in1"][1],
+                       act=ops.ACT_GEGLU)
+            u0 = t0          # the block input `tok` is dead once attn1's output projection has consumed it
+            self._gemm(bl, lambda: [ops.SegSpec(ffh.t)], P[qt + "ff_in2"][0], u0, M, bias=P[qt + "ff_in2"][1],
+                       residual=t2, rowbias=emb_t, rb_div=HW, rb_mod=T)
+            self._ln(bl, u0, P[qt + "norm1"], ln, M)
+            self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qt + "qkv"], qkv, M)
+            self._call(bl, lambda: ops.temporal_attention_d64(qkv.t, B, T, HW, heads, att.t))
+            self.flops += 4.0 * N * HW * T * C
+            self._gemm(bl, lambda: [ops.SegSpec(att.t)], P[qt + "to_out"][0], t1, M, bias=P[qt + "to_out"][1],
+                       residual=u0, rowbias=r_t, rb_div=T * HW, rb_mod=B)
+            self._ln(bl, t1, P[qt + "norm3"], ln, M)
+            self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qt + "ff1"][0], ffh, M, bias=P[qt + "ff1"][1], act=ops.ACT_GEGLU)
+            # x = alpha * x_spatial + (1 - alpha) * x_mix      (video_attention.py:290-294)
+            self._gemm(bl, lambda: [ops.SegSpec(ffh.t)], P[qt + "ff2"][0], t0, M, bias=P[qt + "ff2"][1], residual=t1,
+                       blend_x=t2, alpha=P[n + "alpha"])
+            tok = t0
+        self._gemm(bl, lambda: [ops.SegSpec(tok.t)], P[n + "proj_out"][0], out, M, bias=P[n + "proj_out"][1], residual=x)
+
+    def _ln(self, lst, x: LazyBuf, gb, y: LazyBuf, M, addvec=None, add_div=1, add_mod=1):
+        g, b = gb
+        self._call(lst, lambda: ops.layernorm(x.t, g, b, y.t, M, addvec=addvec, add_div=add_div, add_mod=add_mod))
+
+    # ---- per-video / per-step entry points ------------------------------------------------------------------------
+    def prepare_conditioning(self, context: torch.Tensor, y: torch.Tensor):
+        """context (N|B, 1, ctx) and y (N|B, adm): label_emb(y) and the single-token cross-attention rows."""
+        N, T, B = self.N, self.T, self.B
+        if context.dim() != 3 or context.shape[1] != 1:
+            raise NotImplementedError(f"context of shape {tuple(context.shape)}: the Hi3D path has exactly one "
+                                      f"conditioning token (SURVEY F7); multi-token cross-attention is not built")
+        ctx = context[:, 0]
+        if ctx.shape[0] == B and B != N:
+            ctx = ctx.repeat_interleave(T, dim=0)         # video_model.py:463-465
+        if y.shape[0] == B and B != N:
+            y = y.repeat_interleave(T, dim=0)             # video_model.py:460-462
+        assert ctx.shape[0] == N and y.shape[0] == N
+        self.ctx_in.copy_(ctx)
+        self.ctx_first.copy_(ctx[::T])                    # video_attention.py:250
+        self.y_in.copy_(y)
+        for s in self.cond_steps:
+            s()
+
+    def set_timesteps(self, t: torch.Tensor):
+        self.t_in.copy_(t.reshape(-1).float())
+
+    def run(self):
+        for s in self.steps:
+            s()
+
+    def launches_per_step(self) -> int:
+        from . import _native
+        a = _native.launch_count()
+        self.run()
+        return _native.launch_count() - a
