@@ -20,7 +20,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
 template <typename TC>
 __global__ void sampler_pre_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
                                    const TC* __restrict__ cuc, const TC* __restrict__ cc, int F, int Cx, int Cc, int HW,
-                                   int Cpad, __half* __restrict__ out) {
+                                   int Cpad, __half* __restrict__ out, float* __restrict__ c_noise_out) {
   // one thread per (sample n in [0, 2F), pixel): writes Cpad channels (16-byte vectors)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)2 * F * HW) return;
@@ -29,6 +29,7 @@ __global__ void sampler_pre_kernel(const float* __restrict__ x, const float* __r
   const bool cond = n >= F;
   const float sg = sigma[f];
   const float c_in = rsqrtf(sg * sg + 1.f);
+  if (pix == 0 && c_noise_out != nullptr) c_noise_out[n] = 0.25f * logf(sg);   // VScalingWithEDMcNoise c_noise
   const TC* cat = cond ? cc : cuc;
   __half* o = out + idx * Cpad;
   for (int c0 = 0; c0 < Cpad; c0 += 8) {
@@ -154,7 +155,7 @@ extern "C" int hi3d_timestep_embedding(const float* t, int n, int dim, float max
 
 extern "C" int hi3d_sampler_pre(const float* x, const float* sigma, const void* concat_uc, const void* concat_c,
                                 int concat_is_fp32, int F, int Cx, int Cc, int H, int W, int Cpad, void* out,
-                                void* stream) {
+                                float* c_noise_out, void* stream) {
   if (!x || !sigma || !out || F <= 0 || Cx <= 0 || Cc < 0 || H <= 0 || W <= 0 || (Cpad % 8) || Cpad < Cx + Cc ||
       ((uintptr_t)out & 15) || (Cc > 0 && !concat_c)) {
     set_error("hi3d_sampler_pre: bad arguments (F=%d Cx=%d Cc=%d Cpad=%d)", F, Cx, Cc, Cpad);
@@ -165,11 +166,11 @@ extern "C" int hi3d_sampler_pre(const float* x, const float* sigma, const void* 
   if (concat_is_fp32)
     sampler_pre_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, sigma, (const float*)concat_uc,
                                                                        (const float*)concat_c, F, Cx, Cc, H * W, Cpad,
-                                                                       (__half*)out);
+                                                                       (__half*)out, c_noise_out);
   else
     sampler_pre_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, sigma, (const __half*)concat_uc,
                                                                         (const __half*)concat_c, F, Cx, Cc, H * W, Cpad,
-                                                                        (__half*)out);
+                                                                        (__half*)out, c_noise_out);
   return check_launch("hi3d_sampler_pre");
 }
 

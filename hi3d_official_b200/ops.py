@@ -180,7 +180,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, out: torch.Tensor, max_period:
 
 
 def sampler_pre(x: torch.Tensor, sigma: torch.Tensor, concat_uc: Optional[torch.Tensor], concat_c: Optional[torch.Tensor],
-                out: torch.Tensor):
+                out: torch.Tensor, c_noise_out: Optional[torch.Tensor] = None):
     _chk32(x, "x"); _chk32(sigma, "sigma"); _chk16(out, "out")
     F_, Cx, H, W = x.shape
     Cc, is32 = 0, 0
@@ -191,7 +191,8 @@ def sampler_pre(x: torch.Tensor, sigma: torch.Tensor, concat_uc: Optional[torch.
             if t is not None and (not t.is_contiguous() or t.dtype != concat_c.dtype or tuple(t.shape) != (F_, Cc, H, W)):
                 raise ValueError("concat tensors must be contiguous NCHW of identical dtype/shape [F, Cc, H, W]")
     N.check(N.load().hi3d_sampler_pre(x.data_ptr(), sigma.data_ptr(), _ptr(concat_uc), _ptr(concat_c), is32, F_, Cx, Cc,
-                                      H, W, out.shape[-1], out.data_ptr(), _stream()), "hi3d_sampler_pre")
+                                      H, W, out.shape[-1], out.data_ptr(), _ptr(c_noise_out), _stream()),
+            "hi3d_sampler_pre")
 
 
 def sampler_post(net: torch.Tensor, x: torch.Tensor, sigma: torch.Tensor, sigma_next: torch.Tensor,

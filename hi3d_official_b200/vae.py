@@ -1,0 +1,342 @@
+"""AutoencoderKL (2-D, per frame): drop-in for `sgm.models.autoencoder.AutoencoderKL` /
+`AutoencoderKLModeOnly` (autoencoder.py:436-520,606-619) with the Encoder / Decoder of
+sgm/modules/diffusionmodules/model.py:487-748 compiled into a flat launch plan of the same C-ABI kernels as
+the UNet: GN(eps 1e-6)+swish -> implicit-GEMM conv3x3 (nin_shortcut folded in as extra K segments),
+asymmetric-pad stride-2 down conv, nearest-x2 fused into the up conv's gather, and the single-head d=512 mid
+attention as two GEMMs around a row softmax.  State-dict keys/shapes are the reference's.
+
+`encode(x)` / `decode(z)` take and return NCHW tensors like the reference; all compute is fp16 with fp32
+accumulation (the reference runs the first stage in pure fp16: `disable_first_stage_autocast`).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops, pack
+from .spec import VAEConfig, vae_param_shapes
+from .unet import Arena, LazyBuf, _ParamTree
+
+F16 = torch.float16
+CIN_PAD = 64
+COUT_PAD = 8
+
+
+class _VAEPlan:
+    """Launch plan for encoder or decoder at one (n, H, W)."""
+
+    def __init__(self, ae: "AutoencoderKL", which: str, n: int, H: int, W: int):
+        self.ae, self.which, self.n, self.H, self.W = ae, which, n, H, W
+        self.P = ae._pack()
+        self.dev = ae.device
+        self.A = Arena(self.dev)
+        self._build: List = []
+        self.flops = 0.0
+        self.gn_ws = ops.groupnorm_ws(n, self.dev)
+        self._pp = 0
+        if which == "enc":
+            self._compile_encoder()
+        else:
+            self._compile_decoder()
+        self.A.materialise()
+        self.steps = [b() for b in self._build]
+        self._build = None
+
+    # -- emit helpers ------------------------------------------------------------------------------------------
+    def _gemm(self, segs_fn, W, out, M, **kw):
+        def build():
+            def res(v):
+                return v.t if isinstance(v, LazyBuf) else (v() if callable(v) else v)
+            k2 = {k: res(v) for k, v in kw.items()}
+            g = ops.Gemm(segs_fn(), res(W), res(out), M, engine=self.ae.engine, **k2)
+            self.flops += g.flops
+            return g
+        self._build.append(build)
+
+    def _call(self, fn):
+        self._build.append(lambda: fn)
+
+    def _nxt(self, rows, C):
+        self._pp ^= 1
+        return self.A.want(f"blk{self._pp}", rows, C)
+
+    def _gn(self, x: LazyBuf, key: str, rows_per_img: int, y: LazyBuf, silu=True):
+        g, b = self.P[key]
+        self._call(lambda: ops.groupnorm_silu(x.t, None, self.n, rows_per_img, g, b, 1e-6, silu, y.t, self.gn_ws))
+
+    def _conv(self, src: LazyBuf, key: str, out: LazyBuf, ho, wo, hs, ws, stride=1, ups=0, pad_lo=1, **kw):
+        Wt, b = self.P[key]
+        self._gemm(lambda: ops.conv_taps([src.t], pad_lo=pad_lo), Wt, out, self.n * ho * wo, mode=ops.ROWS_CONV2D,
+                   geom=dict(Ho=ho, Wo=wo, Hs=hs, Ws=ws, stride=stride, ups=ups), bias=b, **kw)
+
+    def _resnet(self, pre: str, x: LazyBuf, cin: int, cout: int, h: int, w: int) -> LazyBuf:
+        """ResnetBlock.forward, model.py:131-151 (temb is None)."""
+        M = self.n * h * w
+        g1, hb, g2 = self.A.want("gn", M, cin), self.A.want("h", M, cout), self.A.want("gn", M, cout)
+        out = self._nxt(M, cout)
+        self._gn(x, pre + "norm1", h * w, g1)
+        self._conv(g1, pre + "conv1", hb, h, w, h, w)
+        self._gn(hb, pre + "norm2", h * w, g2)
+        Wt, b = self.P[pre + "conv2"]
+        geo = dict(Ho=h, Wo=w, Hs=h, Ws=w)
+        if cin != cout:    # nin_shortcut 1x1 as one more K segment over the raw input
+            self._gemm(lambda: ops.conv_taps([g2.t]) + [ops.SegSpec(x.t)], Wt, out, M, mode=ops.ROWS_CONV2D, geom=geo,
+                       bias=b)
+        else:
+            self._gemm(lambda: ops.conv_taps([g2.t]), Wt, out, M, mode=ops.ROWS_CONV2D, geom=geo, bias=b, residual=x)
+        return out
+
+    def _attn(self, pre: str, x: LazyBuf, C: int, h: int, w: int) -> LazyBuf:
+        """AttnBlock.forward, model.py:180-201: one head, d = C, softmax(q k^T * C^-0.5) v per image, as
+        scores = GEMM(q, k) -> row softmax -> GEMM(P, v^T) on the same engine as everything else."""
+        n, L = self.n, h * w
+        M = n * L
+        if L % 64:
+            raise NotImplementedError(f"VAE attention needs (H/8)*(W/8) % 64 == 0, got {L}")
+        A = self.A
+        g, q, k, v, o = (A.want(t, M, C) for t in ("gn", "q", "k", "v", "att"))
+        S, vt = A.want("scores", L, L), A.want("vt", C, L)
+        out = self._nxt(M, C)
+        self._gn(x, pre + "norm", L, g, silu=False)
+        for nm, dst in (("q", q), ("k", k), ("v", v)):
+            Wt, b = self.P[pre + nm]
+            self._gemm(lambda: [ops.SegSpec(g.t)], Wt, dst, M, bias=b)
+        for i in range(n):
+            sl = slice(i * L, (i + 1) * L)
+            self._call(lambda sl=sl: ops.transpose(v.t[sl], L, C, C, vt.t))
+            self._gemm(lambda sl=sl: [ops.SegSpec(q.t[sl])], lambda sl=sl: k.t[sl], S, L)
+            self._call(lambda: ops.softmax_rows(S.t, L, L, float(C) ** -0.5))
+            self._gemm(lambda: [ops.SegSpec(S.t)], vt, lambda sl=sl: o.t[sl], L)
+        Wo, bo = self.P[pre + "proj_out"]
+        self._gemm(lambda: [ops.SegSpec(o.t)], Wo, out, M, bias=bo, residual=x)
+        return out
+
+    # -- encoder / decoder walks ----------------------------------------------------------------------------------
+    def _compile_encoder(self):
+        """Encoder.forward, model.py:576-601 + quant_conv (autoencoder.py:470-471)."""
+        cfg, n, H, W, A = self.ae.cfg, self.n, self.H, self.W, self.A
+        nres = len(cfg.ch_mult)
+        if H % (1 << (nres - 1)) or W % (1 << (nres - 1)):
+            raise ValueError(f"image size {H}x{W} must be divisible by {1 << (nres - 1)}")
+        self.xin = A.want("xin", n * H * W, CIN_PAD)
+        h, w = H, W
+        cur = self._nxt(n * h * w, cfg.ch)
+        self._conv(self.xin, "encoder.conv_in", cur, h, w, h, w)
+        in_mult = (1,) + tuple(cfg.ch_mult)
+        bi = cfg.ch
+        for lvl in range(nres):
+            bi, bo = cfg.ch * in_mult[lvl], cfg.ch * cfg.ch_mult[lvl]
+            for b in range(cfg.num_res_blocks):
+                cur = self._resnet(f"encoder.down.{lvl}.block.{b}.", cur, bi, bo, h, w)
+                bi = bo
+            if lvl != nres - 1:   # Downsample: F.pad (0,1,0,1) + conv3x3 stride 2 pad 0 (model.py:84-88)
+                out = self._nxt(n * (h // 2) * (w // 2), bi)
+                self._conv(cur, f"encoder.down.{lvl}.downsample.conv", out, h // 2, w // 2, h, w, stride=2, pad_lo=0)
+                cur, h, w = out, h // 2, w // 2
+        cur = self._resnet("encoder.mid.block_1.", cur, bi, bi, h, w)
+        cur = self._attn("encoder.mid.attn_1.", cur, bi, h, w)
+        cur = self._resnet("encoder.mid.block_2.", cur, bi, bi, h, w)
+        M = n * h * w
+        g = A.want("gn", M, bi)
+        self._gn(cur, "encoder.norm_out", h * w, g)
+        mom = A.want("h", M, 64)     # conv_out output, padded to 64 channels so quant_conv (1x1) sees one K segment
+        self._conv(g, "encoder.conv_out", mom, h, w, h, w)
+        self.out = A.want("moments", M, COUT_PAD)
+        Wq, bq = self.P["quant_conv"]
+        self._gemm(lambda: [ops.SegSpec(mom.t)], Wq, self.out, M, bias=bq)
+        self.out_hw = (h, w)
+
+    def _compile_decoder(self):
+        """post_quant_conv (autoencoder.py:492) + Decoder.forward, model.py:715-748.  (H, W) are LATENT dims."""
+        cfg, n, h, w, A = self.ae.cfg, self.n, self.H, self.W, self.A
+        nres = len(cfg.ch_mult)
+        self.xin = A.want("xin", n * h * w, CIN_PAD)
+        zq = A.want("h", n * h * w, CIN_PAD)
+        Wp, bp = self.P["post_quant_conv"]
+        self._gemm(lambda: [ops.SegSpec(self.xin.t)], Wp, zq, n * h * w, bias=bp)
+        bi = cfg.ch * cfg.ch_mult[-1]
+        cur = self._nxt(n * h * w, bi)
+        self._conv(zq, "decoder.conv_in", cur, h, w, h, w)
+        cur = self._resnet("decoder.mid.block_1.", cur, bi, bi, h, w)
+        cur = self._attn("decoder.mid.attn_1.", cur, bi, h, w)
+        cur = self._resnet("decoder.mid.block_2.", cur, bi, bi, h, w)
+        for lvl in reversed(range(nres)):
+            bo = cfg.ch * cfg.ch_mult[lvl]
+            for b in range(cfg.num_res_blocks + 1):
+                cur = self._resnet(f"decoder.up.{lvl}.block.{b}.", cur, bi, bo, h, w)
+                bi = bo
+            if lvl != 0:          # Upsample: nearest x2 + conv3x3 (model.py:67-71), fused into the gather
+                out = self._nxt(n * 4 * h * w, bi)
+                self._conv(cur, f"decoder.up.{lvl}.upsample.conv", out, 2 * h, 2 * w, h, w, ups=1)
+                cur, h, w = out, 2 * h, 2 * w
+        M = n * h * w
+        g = A.want("gn", M, bi)
+        self._gn(cur, "decoder.norm_out", h * w, g)
+        self.out = A.want("img", M, COUT_PAD)
+        self._conv(g, "decoder.conv_out", self.out, h, w, h, w)
+        self.out_hw = (h, w)
+
+    def run(self):
+        for s in self.steps:
+            s()
+
+
+class _Net(nn.Module):
+    """Parameter holder exposing `.encoder` / `.decoder` style attribute access for isinstance-free callers."""
+
+
+class Encoder(_ParamTree):
+    pass
+
+
+class Decoder(_ParamTree):
+    pass
+
+
+class AutoencoderKL(nn.Module):
+    """sgm.models.autoencoder.AutoencoderKL: `embed_dim`, `ddconfig` (+ ignored training kwargs such as
+    lossconfig / monitor / ckpt_path=None).  regularizer = DiagonalGaussianRegularizer(sample=True)."""
+    sample_posterior = True
+
+    def __init__(self, embed_dim: int = 4, ddconfig: Optional[dict] = None, **ignored):
+        super().__init__()
+        if ddconfig is None:
+            raise ValueError("ddconfig is required")
+        if ignored.get("ckpt_path") is not None:
+            raise NotImplementedError("ckpt_path in the first-stage config: load weights with load_state_dict")
+        self.cfg = VAEConfig.from_ddconfig(ddconfig, embed_dim)
+        self.embed_dim = embed_dim
+        self.encoder, self.decoder = Encoder(), Decoder()
+        self.quant_conv, self.post_quant_conv = _ParamTree(), _ParamTree()
+        roots = {"encoder": self.encoder, "decoder": self.decoder, "quant_conv": self.quant_conv,
+                 "post_quant_conv": self.post_quant_conv}
+        for name, shp in vae_param_shapes(self.cfg).items():
+            root, rest = name.split(".", 1)
+            roots[root].put(rest, nn.Parameter(torch.empty(shp), requires_grad=False))
+        self._packed = None
+        self._plans: Dict[tuple, _VAEPlan] = {}
+        self.engine = "mma"
+        self.max_batch_size = ignored.get("max_batch_size", None)
+
+    # -- lifecycle ----------------------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._packed, self._plans = None, {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed, self._plans = None, {}
+        return super().load_state_dict(*a, **k)
+
+    def set_engine(self, engine: str):
+        if engine != self.engine:
+            self.engine, self._plans = engine, {}
+
+    @property
+    def device(self):
+        return self.quant_conv.weight.device
+
+    def _pack(self) -> dict:
+        if self._packed is not None:
+            return self._packed
+        if self.device.type != "cuda":
+            raise RuntimeError("hi3d_official_b200.AutoencoderKL computes only on CUDA; there is no CPU fallback")
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        P = {}
+        for k in sd:
+            if not k.endswith(".weight"):
+                continue
+            base = k[:-7]
+            w, b = sd[k], sd[base + ".bias"]
+            if w.dim() == 1:                                   # GroupNorm affine
+                P[base] = (w.float().contiguous(), b.float().contiguous())
+            elif base.endswith("nin_shortcut"):
+                continue                                       # folded into conv2 below
+            elif base in ("encoder.conv_in",):
+                P[base] = (pack.pack_conv2d(w, cin_pad=CIN_PAD), b.float().contiguous())
+            elif base == "decoder.conv_in":
+                P[base] = (pack.pack_conv2d(w, cin_pad=CIN_PAD), b.float().contiguous())
+            elif base == "encoder.conv_out":                   # 2*z channels -> padded to 64 (feeds quant_conv)
+                P[base] = (pack.pack_conv2d(w, cout_pad=64), pack.pack_bias(b, w.shape[0], 64))
+            elif base == "decoder.conv_out":
+                P[base] = (pack.pack_conv2d(w, cout_pad=COUT_PAD), pack.pack_bias(b, w.shape[0], COUT_PAD))
+            elif base == "quant_conv":                         # 1x1: K padded to 64, N padded to 8
+                P[base] = (pack.pack_conv2d(w, cin_pad=64, cout_pad=COUT_PAD), pack.pack_bias(b, w.shape[0], COUT_PAD))
+            elif base == "post_quant_conv":                    # 1x1: K padded to 64, N padded to 64 (feeds conv_in)
+                P[base] = (pack.pack_conv2d(w, cin_pad=CIN_PAD, cout_pad=CIN_PAD), pack.pack_bias(b, w.shape[0], CIN_PAD))
+            elif base.endswith("conv2") and (base[:-5] + "nin_shortcut.weight") in sd:
+                ws_, bs_ = sd[base[:-5] + "nin_shortcut.weight"], sd[base[:-5] + "nin_shortcut.bias"]
+                P[base] = (pack.cat_k(pack.pack_conv2d(w), pack.pack_conv2d(ws_)), (b.float() + bs_.float()).contiguous())
+            else:
+                P[base] = (pack.pack_conv2d(w), b.float().contiguous())
+        self._packed = P
+        return P
+
+    def _plan(self, which: str, n: int, H: int, W: int) -> _VAEPlan:
+        key = (which, n, H, W, self.engine)
+        if key not in self._plans:
+            self._plans[key] = _VAEPlan(self, which, n, H, W)
+        return self._plans[key]
+
+    # -- reference API --------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_moments(self, x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[int, int]]:
+        n, c, H, W = x.shape
+        plan = self._plan("enc", n, H, W)
+        ops.nchw_to_nhwc(x.contiguous(), plan.xin.t.view(n, H, W, CIN_PAD))
+        plan.run()
+        return plan.out.t, plan.out_hw
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_reg_log: bool = False, noise: Optional[torch.Tensor] = None,
+               scale: float = 1.0):
+        """autoencoder.py:468-488.  Posterior sampling draws CPU randn exactly like the reference
+        (distributions.py:37-41) unless `noise` is supplied; AutoencoderKLModeOnly returns the mode."""
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        bs = self.max_batch_size or x.shape[0]
+        outs = []
+        for i in range(0, x.shape[0], bs):
+            xb = x[i:i + bs]
+            mom, (h, w) = self.encode_moments(xb)
+            z = torch.empty(xb.shape[0], self.embed_dim, h, w, dtype=torch.float32, device=x.device)
+            nz = None
+            if self.sample_posterior:
+                nz = noise[i:i + bs] if noise is not None else torch.randn(z.shape).to(device=x.device)
+                nz = nz.float().contiguous()
+            ops.gaussian_sample(mom, nz, z, scale)
+            outs.append(z)
+        z = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        z = z.to(x.dtype)
+        return (z, {}) if return_reg_log else z
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, scale: float = 1.0, **decoder_kwargs) -> torch.Tensor:
+        """autoencoder.py:490-505 (post_quant_conv + decoder); returns NCHW in z's dtype."""
+        if decoder_kwargs:
+            raise NotImplementedError(f"decoder kwargs {list(decoder_kwargs)} (VideoDecoder) are not on the Hi3D path")
+        if z.dtype not in (torch.float16, torch.float32):
+            z = z.float()
+        bs = self.max_batch_size or z.shape[0]
+        outs = []
+        for i in range(0, z.shape[0], bs):
+            zb = z[i:i + bs].contiguous()
+            n, c, h, w = zb.shape
+            plan = self._plan("dec", n, h, w)
+            ops.nchw_to_nhwc(zb, plan.xin.t.view(n, h, w, CIN_PAD), scale)
+            plan.run()
+            H, W = plan.out_hw
+            img = torch.empty(n, self.cfg.out_ch, H, W, dtype=z.dtype, device=z.device)
+            ops.nhwc_to_nchw(plan.out.t, img)
+            outs.append(img)
+        return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+
+    def forward(self, x: torch.Tensor, **kw):
+        z = self.encode(x)
+        return z, self.decode(z), {}
+
+
+class AutoencoderKLModeOnly(AutoencoderKL):
+    """autoencoder.py:606-619: DiagonalGaussianRegularizer(sample=False)."""
+    sample_posterior = False

@@ -142,9 +142,11 @@ int hi3d_timestep_embedding(const float* t, int n, int dim, float max_period, vo
 /* Build the UNet input for one CFG-batched step: prepare_inputs (guiders.py:88-99) + Denoiser c_in scaling
  * (denoiser.py:33-37) + OpenAIWrapper concat (wrappers.py:27) + NCHW->NHWC fp16.
  * x fp32 NCHW [F, Cx, H, W]; sigma fp32 [F]; concat_uc / concat_c fp16-or-fp32 NCHW [F, Cc, H, W] (concat_uc may be
- * NULL == zeros); out fp16 NHWC [2F, H, W, Cpad] (channels [x*c_in | concat | 0-pad]); first F samples = uc half. */
+ * NULL == zeros); out fp16 NHWC [2F, H, W, Cpad] (channels [x*c_in | concat | 0-pad]); first F samples = uc half.
+ * c_noise_out (optional) fp32 [2F] receives c_noise = 0.25*ln(sigma) (denoiser_scaling.py:58), the UNet `timesteps`. */
 int hi3d_sampler_pre(const float* x, const float* sigma, const void* concat_uc, const void* concat_c,
-                     int concat_is_fp32, int F, int Cx, int Cc, int H, int W, int Cpad, void* out, void* stream);
+                     int concat_is_fp32, int F, int Cx, int Cc, int H, int W, int Cpad, void* out, float* c_noise_out,
+                     void* stream);
 
 /* Finish the step: denoised = net*c_out + x*c_skip per half (denoiser.py:36-39), CFG combine with the per-frame
  * scale (guiders.py:78-86), d = (x - denoised)/sigma and Euler update x += d*(sigma_next - sigma)
