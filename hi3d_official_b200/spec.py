@@ -302,17 +302,50 @@ def synth_state_dict(shapes: "Dict[str, Tuple[int, ...]]", seed: int = 0, dtype=
         h = int.from_bytes(hashlib.sha1(k.encode()).digest()[:6], "little") ^ (seed * 0x9E3779B1)
         g = torch.Generator(device="cpu").manual_seed(h & 0x7FFFFFFFFFFF)
         x = torch.randn(tuple(shp), generator=g, dtype=torch.float32)
-        if k.endswith("mix_factor"):
-            x = x * 0.5
-        elif len(shp) == 1:
-            x = 1.0 + 0.1 * x if k.endswith(".weight") else 0.02 * x
-        else:
-            fan_in = 1
-            for d in shp[1:]:
-                fan_in *= d
-            std = gain / (fan_in ** 0.5)
-            if k.endswith(_ZERO_INIT_SUFFIXES):
-                std *= 0.5
-            x = x * std
-        out[k] = x.to(device=device, dtype=dtype)
+        out[k] = _synth_rule(k, x, gain).to(device=device, dtype=dtype)
     return out
+
+
+def _synth_rule(k: str, x: torch.Tensor, gain: float = 1.0) -> torch.Tensor:
+    """Maps a standard-normal tensor to the synthetic distribution of parameter `k`."""
+    shp = x.shape
+    if k.endswith("mix_factor"):
+        return x * 0.5
+    if len(shp) == 1:
+        return 1.0 + 0.1 * x if k.endswith(".weight") else 0.02 * x
+    fan_in = 1
+    for d in shp[1:]:
+        fan_in *= d
+    std = gain / (fan_in ** 0.5)
+    if k.endswith(_ZERO_INIT_SUFFIXES):
+        std *= 0.5
+    return x * std
+
+
+@torch.no_grad()
+def synth_fill_(module: torch.nn.Module, seed: int = 0, fast: bool = False) -> torch.nn.Module:
+    """Fill every parameter of `module` in place with the synthetic recipe.  fast=False reproduces
+    `synth_state_dict` bit-exactly (CPU generator per key, needed wherever results are compared with the
+    oracle); fast=True draws on the parameter's own device (benchmarks: same distribution, different bits)."""
+    if fast:
+        dev_gens = {}
+    for k, p in module.state_dict().items():
+        # engine-level prefixes are stripped so the same keys give the same tensors as the per-network dicts
+        kk = k
+        for pre in ("model.diffusion_model.", "first_stage_model."):
+            if kk.startswith(pre):
+                kk = kk[len(pre):]
+        if fast:
+            g = dev_gens.get(p.device)
+            if g is None:
+                g = dev_gens[p.device] = torch.Generator(device=p.device).manual_seed(1234 + seed)
+            x = torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32)
+        else:
+            h = int.from_bytes(hashlib.sha1(kk.encode()).digest()[:6], "little") ^ (seed * 0x9E3779B1)
+            g = torch.Generator(device="cpu").manual_seed(h & 0x7FFFFFFFFFFF)
+            x = torch.randn(tuple(p.shape), generator=g, dtype=torch.float32)
+        p.copy_(_synth_rule(kk, x).to(device=p.device, dtype=p.dtype))
+    for m in module.modules():          # packed weights / launch plans derived from the old values are stale
+        if hasattr(m, "_packed"):
+            m._packed, m._plans = None, {}
+    return module

@@ -286,7 +286,10 @@ class _Plan:
             return g
         lst.append(build)
 
-    def _call(self, lst, fn):
+    def _call(self, lst, fn, **meta):
+        """meta: kind / flops / bytes = algorithmic work of the launch (read by bench.py's breakdown)."""
+        for k, v in meta.items():
+            setattr(fn, k, v)
         lst.append(lambda: fn)
 
     def _compile(self):
@@ -376,7 +379,8 @@ class _Plan:
         g = A.want("gn", M, cur[1])
         gam, bet = P["out.gn"]
         src = cur[0]
-        self._call(bl, lambda: ops.groupnorm_silu(src.t, None, N, h * w, gam, bet, 1e-5, True, g.t, self.gn_ws))
+        self._call(bl, lambda: ops.groupnorm_silu(src.t, None, N, h * w, gam, bet, 1e-5, True, g.t, self.gn_ws),
+                   kind="groupnorm", bytes=6.0 * M * cur[1])
         self.net_out = A.want("net_out", M, COUT_PAD)
         self._conv(bl, [g], P["out.conv"], self.net_out, h, w, h, w)
 
@@ -417,12 +421,14 @@ class _Plan:
         ws = self.gn_ws
         # -- spatial half
         gam, bet = P[n + "gn1"]
-        self._call(bl, lambda: ops.groupnorm_silu(x1.t, x2.t if x2 else None, N, HW, gam, bet, 1e-5, True, g_in.t, ws))
+        self._call(bl, lambda: ops.groupnorm_silu(x1.t, x2.t if x2 else None, N, HW, gam, bet, 1e-5, True, g_in.t, ws),
+                   kind="groupnorm", bytes=6.0 * M * cin)
         emb1 = self._emb_slice(n)
         self._gemm(bl, lambda: ops.conv_taps([g_in.t]), P[n + "conv1"][0], hbuf, M, mode=ops.ROWS_CONV2D,
                    geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv1"][1], rowbias=emb1, rb_div=HW, rb_mod=N)
         gam2, bet2 = P[n + "gn2"]
-        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, N, HW, gam2, bet2, 1e-5, True, g_mid.t, ws))
+        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, N, HW, gam2, bet2, 1e-5, True, g_mid.t, ws),
+                   kind="groupnorm", bytes=6.0 * M * cout)
         if cin != cout:
             self._gemm(bl, lambda: ops.conv_taps([g_mid.t]) + [ops.SegSpec(s.t) for s in srcs], P[n + "conv2"][0], xs, M,
                        mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1])
@@ -433,13 +439,15 @@ class _Plan:
         # -- temporal half: statistics over (T, H, W) per clip, 3-tap conv along frames
         q = n + "time_stack."
         g3, b3 = P[q + "gn1"]
-        self._call(bl, lambda: ops.groupnorm_silu(xs.t, None, B, T * HW, g3, b3, 1e-5, True, g_mid.t, ws))
+        self._call(bl, lambda: ops.groupnorm_silu(xs.t, None, B, T * HW, g3, b3, 1e-5, True, g_mid.t, ws),
+                   kind="groupnorm", bytes=6.0 * M * cout)
         geo = dict(Ho=HW, Wo=1, T=T)
         emb2 = self._emb_slice(q)
         self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv1"][0], hbuf, M, mode=ops.ROWS_TEMPORAL, geom=geo,
                    bias=P[q + "conv1"][1], rowbias=emb2, rb_div=HW, rb_mod=N)
         g4, b4 = P[q + "gn2"]
-        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, B, T * HW, g4, b4, 1e-5, True, g_mid.t, ws))
+        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, B, T * HW, g4, b4, 1e-5, True, g_mid.t, ws),
+                   kind="groupnorm", bytes=6.0 * M * cout)
         # x_t = xs + conv(...);  out = alpha*xs + (1-alpha)*x_t   (util.py:358-369)
         self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv2"][0], out, M, mode=ops.ROWS_TEMPORAL, geom=geo,
                    bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"])
@@ -466,7 +474,8 @@ class _Plan:
         ops.Gemm([ops.SegSpec(tpe_h)], P[n + "tpe2"][0], emb_t, T, bias=P[n + "tpe2"][1])()
 
         gam, bet = P[n + "norm"]
-        self._call(bl, lambda: ops.groupnorm_silu(x.t, None, N, HW, gam, bet, 1e-6, False, gn.t, ws))
+        self._call(bl, lambda: ops.groupnorm_silu(x.t, None, N, HW, gam, bet, 1e-6, False, gn.t, ws),
+                   kind="groupnorm", bytes=6.0 * M * C)
         self._gemm(bl, lambda: [ops.SegSpec(gn.t)], P[n + "proj_in"][0], t0, M, bias=P[n + "proj_in"][1])
         tok = t0
         for d in range(self.net.cfg.transformer_depth):
@@ -481,7 +490,8 @@ class _Plan:
             # ---- spatial BasicTransformerBlock (attention.py:551-572)
             self._ln(bl, tok, P[qs + "norm1"], ln, M)
             self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qs + "qkv"], qkv, M)
-            self._call(bl, lambda: ops.attention_d64(qkv.t, N, HW, heads, att.t))
+            self._call(bl, lambda: ops.attention_d64(qkv.t, N, HW, heads, att.t), kind="spatial_attention",
+                       flops=4.0 * N * HW * HW * C, bytes=8.0 * M * C)
             self.flops += 4.0 * N * HW * HW * C
             self._gemm(bl, lambda: [ops.SegSpec(att.t)], P[qs + "to_out"][0], t1, M, bias=P[qs + "to_out"][1],
                        residual=tok, rowbias=r_s, rb_div=HW, rb_mod=N)
@@ -497,7 +507,8 @@ class _Plan:
                        residual=t2, rowbias=emb_t, rb_div=HW, rb_mod=T)
             self._ln(bl, u0, P[qt + "norm1"], ln, M)
             self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qt + "qkv"], qkv, M)
-            self._call(bl, lambda: ops.temporal_attention_d64(qkv.t, B, T, HW, heads, att.t))
+            self._call(bl, lambda: ops.temporal_attention_d64(qkv.t, B, T, HW, heads, att.t), kind="temporal_attention",
+                       flops=4.0 * N * HW * T * C, bytes=8.0 * M * C)
             self.flops += 4.0 * N * HW * T * C
             self._gemm(bl, lambda: [ops.SegSpec(att.t)], P[qt + "to_out"][0], t1, M, bias=P[qt + "to_out"][1],
                        residual=u0, rowbias=r_t, rb_div=T * HW, rb_mod=B)
@@ -511,7 +522,8 @@ class _Plan:
 
     def _ln(self, lst, x: LazyBuf, gb, y: LazyBuf, M, addvec=None, add_div=1, add_mod=1):
         g, b = gb
-        self._call(lst, lambda: ops.layernorm(x.t, g, b, y.t, M, addvec=addvec, add_div=add_div, add_mod=add_mod))
+        self._call(lst, lambda: ops.layernorm(x.t, g, b, y.t, M, addvec=addvec, add_div=add_div, add_mod=add_mod),
+                   kind="layernorm", bytes=4.0 * M * x.cols)
 
     # ---- per-video / per-step entry points ------------------------------------------------------------------------
     def prepare_conditioning(self, context: torch.Tensor, y: torch.Tensor):
