@@ -1,0 +1,118 @@
+"""tcgen05/TMEM/TMA implicit-GEMM engine (hi3d_gemm_tc5) against PyTorch fp32 and against the mma.sync engine,
+on every geometry it claims (plain rows, 3x3 conv patches with OOB padding, temporal taps, K-concat, skip
+segments) and every epilogue."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from hi3d_official_b200 import ops, pack  # noqa: E402
+from test_kernels_gpu import DEV, H, close, nhwc, rnd  # noqa: E402
+
+E = "tc5"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (300, 320, 320), (1000, 960, 640), (4096, 1280, 1280),
+                                   (257, 2560, 320), (128, 64, 1024)])
+def test_tc5_plain(M, N, K):
+    a = rnd(M, K).to(H)
+    w = rnd(N, K, scale=K ** -0.5).to(H)
+    bias = rnd(N, scale=0.1)
+    rb = rnd(5, N, scale=0.5).to(H)
+    res = rnd(M, N).to(H)
+    out = torch.zeros(M, N, dtype=H, device=DEV)
+    ref0 = a.float() @ w.float().t()
+    ops.Gemm([ops.SegSpec(a)], w, out, M, engine=E)()
+    close(out, ref0, name="plain")
+    ops.Gemm([ops.SegSpec(a)], w, out, M, bias=bias, rowbias=rb, rb_div=7, rb_mod=5, residual=res, engine=E)()
+    idx = (torch.arange(M, device=DEV) // 7) % 5
+    close(out, (ref0 + bias + rb.float()[idx]).to(H).float() + res.float(), name="bias+rowbias+res")
+    bx = rnd(M, N, seed=5).to(H)
+    ops.Gemm([ops.SegSpec(a)], w, out, M, bias=bias, residual=res, blend_x=bx, alpha=0.3, act=ops.ACT_NONE, engine=E)()
+    close(out, 0.3 * bx.float() + 0.7 * ((ref0 + bias).to(H).float() + res.float()), name="blend")
+    ops.Gemm([ops.SegSpec(a)], w, out, M, bias=bias, act=ops.ACT_SILU, engine=E)()
+    close(out, F.silu(ref0 + bias), name="silu")
+
+
+def test_tc5_geglu_and_kconcat():
+    M, C = 513, 320
+    a = rnd(M, C).to(H)
+    w, b = rnd(8 * C, C, scale=C ** -0.5), rnd(8 * C, scale=0.1)
+    wp, bp = pack.pack_geglu(w, b)
+    out = torch.zeros(M, 4 * C, dtype=H, device=DEV)
+    ops.Gemm([ops.SegSpec(a)], wp, out, M, bias=bp, act=ops.ACT_GEGLU, engine=E)()
+    v, g = (a.float() @ w.to(H).float().t() + b).chunk(2, dim=-1)
+    close(out, v * F.gelu(g), name="geglu")
+    a1, a2 = rnd(M, 128).to(H), rnd(M, 64, seed=2).to(H)
+    w2 = rnd(192, 192, scale=192 ** -0.5).to(H)
+    o2 = torch.zeros(M, 192, dtype=H, device=DEV)
+    ops.Gemm([ops.SegSpec(a1), ops.SegSpec(a2)], w2, o2, M, engine=E)()
+    close(o2, torch.cat([a1, a2], 1).float() @ w2.float().t(), name="kconcat")
+
+
+@pytest.mark.parametrize("n,ci,co,hh,ww", [(4, 64, 128, 16, 16), (2, 128, 320, 32, 32), (8, 64, 64, 8, 8), (32, 64, 64, 4, 4),
+                                           (2, 64, 128, 64, 64)])
+def test_tc5_conv3x3(n, ci, co, hh, ww):
+    x = rnd(n, ci, hh, ww)
+    w = rnd(co, ci, 3, 3, scale=(9 * ci) ** -0.5)
+    b = rnd(co, scale=0.1)
+    emb = rnd(n, co, scale=0.5).to(H)
+    xh = nhwc(x)
+    ref = F.conv2d(xh.permute(0, 3, 1, 2).float(), w.to(H).float(), b, padding=1) + emb.float()[:, :, None, None]
+    M = n * hh * ww
+    out = torch.zeros(M, co, dtype=H, device=DEV)
+    ops.Gemm(ops.conv_taps([xh]), pack.pack_conv2d(w), out, M, mode=ops.ROWS_CONV2D, geom=dict(Ho=hh, Wo=ww, Hs=hh, Ws=ww),
+             bias=b, rowbias=emb, rb_div=hh * ww, rb_mod=n, engine=E)()
+    close(out.view(n, hh, ww, co).permute(0, 3, 1, 2), ref, name="conv3x3")
+
+
+def test_tc5_conv_concat_skip():
+    n, c1, c2, co, hh, ww = 4, 64, 128, 64, 16, 16
+    x1, x2, hcur = rnd(n, c1, hh, ww), rnd(n, c2, hh, ww, seed=2), rnd(n, co, hh, ww, seed=3)
+    w3 = rnd(co, co, 3, 3, scale=(9 * co) ** -0.5)
+    ws_ = rnd(co, c1 + c2, 1, 1, scale=(c1 + c2) ** -0.5)
+    b3 = rnd(co, scale=0.1)
+    x1h, x2h, hh_ = nhwc(x1), nhwc(x2), nhwc(hcur)
+    segs = ops.conv_taps([hh_]) + [ops.SegSpec(x1h), ops.SegSpec(x2h)]
+    W = pack.cat_k(pack.pack_conv2d(w3), pack.pack_conv2d(ws_))
+    M = n * hh * ww
+    out = torch.zeros(M, co, dtype=H, device=DEV)
+    ops.Gemm(segs, W, out, M, mode=ops.ROWS_CONV2D, geom=dict(Ho=hh, Wo=ww, Hs=hh, Ws=ww), bias=b3, engine=E)()
+    xr = torch.cat([x1h, x2h], -1).permute(0, 3, 1, 2).float()
+    ref = F.conv2d(hh_.permute(0, 3, 1, 2).float(), w3.to(H).float(), b3, padding=1) + F.conv2d(xr, ws_.to(H).float())
+    close(out.view(n, hh, ww, co).permute(0, 3, 1, 2), ref, name="conv+skip")
+    w1 = rnd(co, c1 + c2, 3, 3, scale=(9 * (c1 + c2)) ** -0.5)
+    ops.Gemm(ops.conv_taps([x1h, x2h]), pack.pack_conv2d(w1), out, M, mode=ops.ROWS_CONV2D,
+             geom=dict(Ho=hh, Wo=ww, Hs=hh, Ws=ww), bias=b3, engine=E)()
+    close(out.view(n, hh, ww, co).permute(0, 3, 1, 2), F.conv2d(xr, w1.to(H).float(), b3, padding=1), name="conv concat")
+
+
+@pytest.mark.parametrize("T,hw", [(16, 256), (16, 64), (16, 16), (8, 128)])
+def test_tc5_temporal_conv(T, hw):
+    b, c, co = 2, 64, 128
+    x = rnd(b, c, T, hw, 1)
+    w = rnd(co, c, 3, 1, 1, scale=(3 * c) ** -0.5)
+    bias = rnd(co, scale=0.1)
+    xh = x.permute(0, 2, 3, 4, 1).reshape(b * T * hw, c).contiguous().to(H)
+    M = b * T * hw
+    res = rnd(M, co, seed=7).to(H)
+    out = torch.zeros(M, co, dtype=H, device=DEV)
+    ops.Gemm(ops.temporal_taps(xh), pack.pack_conv3d_t(w), out, M, mode=ops.ROWS_TEMPORAL, geom=dict(Ho=hw, Wo=1, T=T),
+             bias=bias, residual=res, blend_x=res, alpha=0.4, engine=E)()
+    xr = xh.view(b, T, hw, 1, c).permute(0, 4, 1, 2, 3).float()
+    conv = F.conv3d(xr, w.to(H).float(), bias, padding=(1, 0, 0)).permute(0, 2, 3, 4, 1).reshape(M, co)
+    ref = 0.4 * res.float() + 0.6 * (conv.to(H).float() + res.float())
+    close(out, ref, name="temporal conv + blend")
+
+
+def test_tc5_unsupported_geometry_forwards_to_mma_engine():
+    n, ci, co, hs = 2, 64, 64, 12
+    x, w = rnd(n, ci, hs, hs), rnd(co, ci, 3, 3, scale=(9 * ci) ** -0.5)
+    xh = nhwc(x)
+    ref = F.conv2d(xh.permute(0, 3, 1, 2).float(), w.to(H).float(), stride=2, padding=1)
+    ho = ref.shape[2]
+    out = torch.zeros(n * ho * ho, co, dtype=H, device=DEV)
+    ops.Gemm(ops.conv_taps([xh]), pack.pack_conv2d(w), out, n * ho * ho, mode=ops.ROWS_CONV2D,
+             geom=dict(Ho=ho, Wo=ho, Hs=hs, Ws=hs, stride=2), engine=E)()
+    close(out.view(n, ho, ho, co).permute(0, 3, 1, 2), ref, name="stride-2 via fallback")
