@@ -1,15 +1,27 @@
 // GroupNorm(32) [+SiLU] and LayerNorm for channels-last fp16 activations.  Statistics in fp32 (final
 // combine in fp64), matching the reference's fp32 GroupNorm32 / autocast-fp32 LayerNorm.
+// Both are pure HBM streams: every thread owns one fixed 16-byte channel column, keeps its per-channel
+// constants in registers and walks rows with several independent 16-byte loads in flight.
 #include "common.cuh"
 
 namespace hi3d {
 
 constexpr int GN_MAX_CHUNKS = 64;
 constexpr int GN_GROUPS = 32;
+constexpr int GN_UNROLL = 4;
+
+HI3D_DEVINL Half8 ld_stream(const __half* p) {
+  Half8 v;
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+               : "l"(p));
+  *reinterpret_cast<uint4*>(&v) = u;
+  return v;
+}
 
 // ---- pass 1: per-(sample, chunk, group) partial sum / sum of squares -------------------------------
-// grid (chunks, n_samples); blockDim = RL * CV where CV = C/8 vector-columns, so every thread owns one
-// fixed 8-channel column and walks rows with stride RL.
+// grid (chunks, n_samples); blockDim = RL * CV where CV = C/8 vector-columns.
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
                 long long rows_per_chunk, float* __restrict__ ws) {
@@ -31,8 +43,22 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) s[e] = q[e] = 0.f;
-  for (long long r = r0 + rl; r < r1; r += RL) {
-    const Half8 v = *reinterpret_cast<const Half8*>(base + r * ld);
+  long long r = r0 + rl;
+  for (; r + (long long)(GN_UNROLL - 1) * RL < r1; r += (long long)GN_UNROLL * RL) {
+    Half8 v[GN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; u++) v[u] = ld_stream(base + (r + (long long)u * RL) * ld);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; u++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(v[u].h[k]);
+        s[2 * k] += f.x; q[2 * k] += f.x * f.x;
+        s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
+      }
+  }
+  for (; r < r1; r += RL) {
+    const Half8 v = ld_stream(base + r * ld);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const float2 f = __half22float2(v.h[k]);
@@ -58,16 +84,13 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
 }
 
 // ---- pass 2: y = [silu]((x - mean) * rstd * gamma + beta) ------------------------------------------
-// grid (row_slabs, n_samples). Dynamic smem: 2*C floats (per-channel scale / shift).
-__global__ void __launch_bounds__(256)
+// grid (row_slabs, n_samples), blockDim = RL * CV.
+__global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
-                int rows_per_cta, int nchunks, const float* __restrict__ ws, const float* __restrict__ gamma,
+                long long rows_per_cta, int nchunks, const float* __restrict__ ws, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int apply_silu, __half* __restrict__ y) {
-  extern __shared__ float sm[];
   __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
   const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
-  float* sA = sm;
-  float* sB = sm + C;
   const int tid = threadIdx.x, n = blockIdx.y;
   if (tid < GN_GROUPS) {
     double s = 0.0, q = 0.0;
@@ -81,97 +104,118 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
     srstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 256) {
-    const int g = c / cpg;
-    const float a = srstd[g] * gamma[c];
-    sA[c] = a;
-    sB[c] = beta[c] - smean[g] * a;
+  const int cv = tid % CV, rl = tid / CV, RL = blockDim.x / CV;
+  const int c0 = cv * 8;
+  float A[8], B[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const int c = c0 + e, g = c / cpg;
+    A[e] = srstd[g] * gamma[c];
+    B[e] = beta[c] - smean[g] * A[e];
   }
-  __syncthreads();
+  const __half* base;
+  int ld;
+  if (c0 < C1) { base = x1 + c0; ld = C1; } else { base = x2 + (c0 - C1); ld = C2; }
+  const long long srow0 = (long long)n * rows_per_sample;
+  base += srow0 * ld;
+  __half* yb = y + srow0 * C + c0;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
-  long long nrows = rows_per_sample - r0;
-  if (nrows > rows_per_cta) nrows = rows_per_cta;
-  const long long total = nrows * CV;
-  const long long srow0 = (long long)n * rows_per_sample + r0;
-  for (long long idx = tid; idx < total; idx += 256) {
-    const long long r = idx / CV;
-    const int cv = (int)(idx - r * CV);
-    const int c0 = cv * 8;
-    const __half* src = (c0 < C1) ? x1 + (srow0 + r) * C1 + c0 : x2 + (srow0 + r) * C2 + (c0 - C1);
-    Half8 v = *reinterpret_cast<const Half8*>(src);
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  auto xform = [&](Half8 v) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       float2 f = __half22float2(v.h[k]);
-      f.x = f.x * sA[c0 + 2 * k] + sB[c0 + 2 * k];
-      f.y = f.y * sA[c0 + 2 * k + 1] + sB[c0 + 2 * k + 1];
+      f.x = f.x * A[2 * k] + B[2 * k];
+      f.y = f.y * A[2 * k + 1] + B[2 * k + 1];
       if (apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
       v.h[k] = __floats2half2_rn(f.x, f.y);
     }
-    *reinterpret_cast<Half8*>(y + (srow0 + r) * C + c0) = v;
+    return v;
+  };
+  long long r = r0 + rl;
+  for (; r + (long long)(GN_UNROLL - 1) * RL < r1; r += (long long)GN_UNROLL * RL) {
+    Half8 v[GN_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; u++) v[u] = ld_stream(base + (r + (long long)u * RL) * ld);
+#pragma unroll
+    for (int u = 0; u < GN_UNROLL; u++) *reinterpret_cast<Half8*>(yb + (r + (long long)u * RL) * C) = xform(v[u]);
   }
+  for (; r < r1; r += RL) *reinterpret_cast<Half8*>(yb + r * C) = xform(ld_stream(base + r * ld));
 }
 
-// ---- LayerNorm: one warp per row, row kept in registers ----------------------------------------------
-template <int VPL>
+// ---- LayerNorm: one warp per LN_ROWS rows, rows kept in registers --------------------------------------------
+template <int VPL, int ROWS>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ addvec, int add_div, int add_mod, long long M,
                  int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  __half* __restrict__ y) {
   const int lane = threadIdx.x & 31;
-  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (m >= M) return;
+  const long long m0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS;
+  if (m0 >= M) return;
   const int CV = C >> 3;
-  const __half* row = x + m * C;
-  const __half* av = addvec ? addvec + (long long)((m / add_div) % add_mod) * C : nullptr;
-  float v[VPL][8];
-  float sum = 0.f;
+  Half8 raw[ROWS][VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; i++) {
-    const int cv = lane + 32 * i;
-    if (cv < CV) {
-      const Half8 h = *reinterpret_cast<const Half8*>(row + cv * 8);
+  for (int r = 0; r < ROWS; r++)
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const float2 f = __half22float2(h.h[k]);
-        v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
-      }
-      if (av) {
-        const Half8 a = *reinterpret_cast<const Half8*>(av + cv * 8);
+    for (int i = 0; i < VPL; i++) {
+      const int cv = lane + 32 * i;
+      if (cv < CV && m0 + r < M) raw[r][i] = ld_stream(x + (m0 + r) * C + cv * 8);
+    }
+#pragma unroll
+  for (int r = 0; r < ROWS; r++) {
+    const long long m = m0 + r;
+    if (m >= M) break;
+    const __half* av = addvec ? addvec + (long long)((m / add_div) % add_mod) * C : nullptr;
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      const int cv = lane + 32 * i;
+      if (cv < CV) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const float2 f = __half22float2(a.h[k]);
-          v[i][2 * k] += f.x; v[i][2 * k + 1] += f.y;
+          const float2 f = __half22float2(raw[r][i].h[k]);
+          v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
         }
+        if (av) {
+          const Half8 a = *reinterpret_cast<const Half8*>(av + cv * 8);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float2 f = __half22float2(a.h[k]);
+            v[i][2 * k] += f.x; v[i][2 * k + 1] += f.y;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) sum += v[i][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[i][e] = 0.f;
       }
-#pragma unroll
-      for (int e = 0; e < 8; e++) sum += v[i][e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; e++) v[i][e] = 0.f;
     }
-  }
-  const float mean = warp_sum(sum) / (float)C;
-  float sq = 0.f;
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; i++) {
-    if (lane + 32 * i < CV) {
+    for (int i = 0; i < VPL; i++) {
+      if (lane + 32 * i < CV) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; sq += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-#pragma unroll
-  for (int i = 0; i < VPL; i++) {
-    const int cv = lane + 32 * i;
-    if (cv < CV) {
-      Half8 o;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int c = cv * 8 + 2 * k;
-        o.h[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * gamma[c] + beta[c],
-                                   (v[i][2 * k + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+        for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; sq += d * d; }
       }
-      *reinterpret_cast<Half8*>(y + m * C + cv * 8) = o;
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      const int cv = lane + 32 * i;
+      if (cv < CV) {
+        Half8 o;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int c = cv * 8 + 2 * k;
+          const float2 gm = *reinterpret_cast<const float2*>(gamma + c), bt = *reinterpret_cast<const float2*>(beta + c);
+          o.h[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * gm.x + bt.x, (v[i][2 * k + 1] - mean) * rstd * gm.y + bt.y);
+        }
+        *reinterpret_cast<Half8*>(y + m * C + cv * 8) = o;
+      }
     }
   }
 }
@@ -187,8 +231,8 @@ extern "C" int64_t hi3d_groupnorm_ws_floats(int n_samples) {
 extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples,
                                    int64_t rows_per_sample, const float* gamma, const float* beta, float eps,
                                    int apply_silu, void* y, float* ws, void* stream) {
-  const int C = C1 + (x2 ? C2 : 0);
   if (!x2) C2 = 0;
+  const int C = C1 + C2;
   if (!x1 || !y || !ws || !gamma || !beta || n_samples <= 0 || rows_per_sample <= 0 || C1 <= 0 || (C1 % 8) || (C2 % 8) ||
       (C % GN_GROUPS) || C > 4096 || ((uintptr_t)x1 & 15) || ((uintptr_t)y & 15) || (x2 && ((uintptr_t)x2 & 15)) ||
       n_samples > 65535) {
@@ -200,9 +244,9 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
   const int CV = C / 8;
   const int threads = (512 / CV) * CV;
   const int RL = threads / CV;
-  // enough CTAs for a few waves, each chunk at least a handful of row-lanes deep
+  // enough CTAs for a few waves; every chunk at least GN_UNROLL row-lane sweeps deep
   long long chunks = (592 + n_samples - 1) / n_samples;
-  const long long max_by_rows = (rows_per_sample + (long long)RL * 4 - 1) / ((long long)RL * 4);
+  const long long max_by_rows = (rows_per_sample + (long long)RL * GN_UNROLL - 1) / ((long long)RL * GN_UNROLL);
   if (chunks > max_by_rows) chunks = max_by_rows;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks < 1) chunks = 1;
@@ -212,11 +256,11 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
                                                                         rows_per_sample, rpc, ws);
   int rc = check_launch("hi3d_groupnorm_silu(stats)");
   if (rc) return rc;
-  int rows_per_cta = 4096 / CV;
-  if (rows_per_cta < 1) rows_per_cta = 1;
-  const long long slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
+  // apply: ~8 row-lane sweeps per CTA, but never fewer CTAs than ~4 waves when the tensor is large enough
+  long long rows_per_cta = (long long)RL * GN_UNROLL * 2;
+  long long slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
   if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_silu: too many slabs"); return -2; }
-  gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), 256, 2 * C * sizeof(float), st>>>(
+  gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
       (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, (int)chunks, ws, gamma, beta, eps,
       apply_silu, (__half*)y);
   return check_launch("hi3d_groupnorm_silu(apply)");
@@ -225,22 +269,25 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
 extern "C" int hi3d_layernorm(const void* x, const void* addvec, int add_div, int add_mod, int64_t M, int C,
                               const float* gamma, const float* beta, float eps, void* y, void* stream) {
   if (!x || !y || !gamma || !beta || M <= 0 || C <= 0 || (C % 8) || C > 2560 || ((uintptr_t)x & 15) ||
-      ((uintptr_t)y & 15) || (addvec && (add_div <= 0 || add_mod <= 0 || ((uintptr_t)addvec & 15)))) {
+      ((uintptr_t)y & 15) || ((uintptr_t)gamma & 7) || ((uintptr_t)beta & 7) ||
+      (addvec && (add_div <= 0 || add_mod <= 0 || ((uintptr_t)addvec & 15)))) {
     set_error("hi3d_layernorm: bad arguments (M=%lld C=%d)", (long long)M, C);
     return -2;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const long long blocks = (M + 7) / 8;
-  if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }
   const int CV = C / 8;
-  if (CV <= 64)
-    layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)addvec, add_div, add_mod, M, C,
-                                                         gamma, beta, eps, (__half*)y);
-  else if (CV <= 160)
-    layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)addvec, add_div, add_mod, M, C,
-                                                         gamma, beta, eps, (__half*)y);
-  else
-    layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, (const __half*)addvec, add_div, add_mod, M,
-                                                          C, gamma, beta, eps, (__half*)y);
+  const __half* xp = (const __half*)x;
+  const __half* ap = (const __half*)addvec;
+  __half* yp = (__half*)y;
+#define HI3D_LN_LAUNCH(VPL, ROWS)                                                                                   \
+  do {                                                                                                              \
+    const long long blocks = (M + 8 * ROWS - 1) / (8 * ROWS);                                                       \
+    if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }                             \
+    layernorm_kernel<VPL, ROWS><<<(unsigned)blocks, 256, 0, st>>>(xp, ap, add_div, add_mod, M, C, gamma, beta, eps, yp); \
+  } while (0)
+  if (CV <= 64) HI3D_LN_LAUNCH(2, 4);
+  else if (CV <= 160) HI3D_LN_LAUNCH(5, 2);
+  else HI3D_LN_LAUNCH(10, 1);
+#undef HI3D_LN_LAUNCH
   return check_launch("hi3d_layernorm");
 }
