@@ -1,15 +1,19 @@
 // Implicit-GEMM engine, Blackwell-native variant: TMA (cp.async.bulk.tensor) operand staging into
-// SWIZZLE_128B shared tiles, tcgen05.mma (UTCHMMA, cta_group::1, M=128) with the fp32 accumulator in TMEM,
+// SWIZZLE_128B shared tiles, tcgen05.mma (UTCHMMA, cta_group::1, M=128) with fp32 accumulators in TMEM,
 // tcgen05.ld epilogue.  Same contract as hi3d_gemm (include/hi3d_b200.h); geometries this engine does not
-// cover (stride-2 / upsample-fused convs, odd tile shapes) are forwarded to the mma.sync engine.
+// cover (stride-2 / upsample-fused convs, odd tile shapes, N < 32) are forwarded to the mma.sync engine.
 //
-// One CTA = one 128 x BN output tile.  The 128 rows of a tile are
+// Persistent kernel: one CTA per SM walks output tiles (n-tile fastest, so the CTAs running together share the
+// same A rows through L2).  A tile is 128 x BN with BN a runtime multiple of 32 (<= 256) chosen so that N is
+// covered with the least padding (N=320 -> 2 x 160, N=960 -> 5 x 192, ...).  The 128 rows of a tile are
 //   PLAIN    : 128 consecutive rows
-//   CONV2D   : a (tn images) x (th rows) x (tw columns) patch, tn*th*tw = 128 -- the 3x3 taps then are the same
-//              TMA box shifted by (dy, dx), and the zero padding is TMA out-of-bounds fill
-//   TEMPORAL : (tf frames) x (ts pixels), tf*ts = 128 -- the temporal taps shift the frame coordinate, clip
-//              boundaries zero-fill by OOB on the frame axis of a [C, HW, T, B] view.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//   CONV2D   : a (tn images) x (th rows) x (tw columns) patch, tn*th*tw = 128 -- the 3x3 taps are the same TMA box
+//              shifted by (dy, dx) and the zero padding is TMA out-of-bounds fill
+//   TEMPORAL : (tf frames) x (ts pixels), tf*ts = 128 -- the temporal taps shift the frame coordinate of a
+//              [C, HW, T, B] view; clip boundaries zero-fill by OOB.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating 32-column chunks).  Two accumulator
+// buffers (TMEM columns [0,256) and [256,512)) let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
 #include <string.h>
 
@@ -20,8 +24,12 @@ int validate_gemm(const hi3d_gemm_params* p, const char* who);
 
 constexpr int T5_BM = 128;
 constexpr int T5_BK = 64;
-constexpr int T5_THREADS = 192;
+constexpr int T5_THREADS = 320;
+constexpr int T5_EPI_WARPS = 8;
 constexpr int T5_MAX_MAPS = 4;
+constexpr int T5_MAX_STAGES = 8;
+constexpr int T5_A_BYTES = T5_BM * 128;
+constexpr int T5_SMEM_BUDGET = 200 * 1024;
 
 struct T5Seg {
   int map;       // index into amap[]
@@ -35,6 +43,7 @@ struct T5Params {
   T5Seg seg[HI3D_MAX_SEGS];
   int nseg;
   int M, N, K, mode;
+  int BN, stages, n_tiles, total_tiles;
   // tile -> rows
   int tw, th, tn;      // CONV2D patch (PLAIN: tw = 128, th = tn = 1; TEMPORAL: tw = ts, th = tf)
   int Wo, Ho, Nimg;    // CONV2D: output W, H, images.  TEMPORAL: Wo = HW, Ho = T, Nimg = B
@@ -59,6 +68,9 @@ HI3D_DEVINL void mbar_init(uint32_t bar, int count) {
 HI3D_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+HI3D_DEVINL void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
 HI3D_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   unsigned long long spins = 0;
@@ -70,7 +82,7 @@ HI3D_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1ull << 26)) __trap();  // watchdog: a lost TMA / MMA completion must not hang the GPU
+    if (!done && ++spins > (1ull << 27)) __trap();  // watchdog: a lost TMA / MMA completion must not hang the GPU
   }
 }
 HI3D_DEVINL void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -122,52 +134,63 @@ HI3D_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-template <int BN, int STAGES>
-struct T5Smem {
-  static constexpr int A_BYTES = T5_BM * 128;
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = T5_BM * (BN + 8) * 2;
-  static constexpr int DATA_BYTES = PIPE_BYTES > STAGING_BYTES ? PIPE_BYTES : STAGING_BYTES;
-  static constexpr int BAR_OFF = DATA_BYTES;              // full[STAGES], empty[STAGES], accum, tmem ptr
-  static constexpr int TOTAL = DATA_BYTES + 128 + 1024;   // + barriers + 1 KB alignment slack
+// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): far below the fp16 rounding of the GEGLU output, and a
+// third of the instructions of erff().  gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).
+HI3D_DEVINL float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+struct T5Tile {
+  int x0, y0, z0;   // TMA origin coordinates (CONV2D: x, y, image; TEMPORAL: pixel, frame, clip)
 };
 
-// tile-local row -> global output row (and validity)
-HI3D_DEVINL long long t5_row(const T5Params& p, int tile, int r) {
+HI3D_DEVINL T5Tile t5_origin(const T5Params& p, int mt) {
+  T5Tile t{0, 0, 0};
+  if (p.mode != HI3D_ROWS_PLAIN) {
+    const int tx = mt % p.tiles_x, rest = mt / p.tiles_x;
+    t.x0 = tx * p.tw;
+    t.y0 = (rest % p.tiles_y) * p.th;
+    t.z0 = (rest / p.tiles_y) * p.tn;
+  }
+  return t;
+}
+// tile-local row -> global output row (or -1)
+HI3D_DEVINL long long t5_row(const T5Params& p, int mt, const T5Tile& o, int r) {
   if (p.mode == HI3D_ROWS_PLAIN) {
-    long long m = (long long)tile * T5_BM + r;
+    const long long m = (long long)mt * T5_BM + r;
     return m < p.M ? m : -1;
   }
-  const int tx = tile % p.tiles_x;
-  const int rest = tile / p.tiles_x;
-  const int ty = rest % p.tiles_y;
-  const int tz = rest / p.tiles_y;
-  const int x = tx * p.tw + r % p.tw;
-  const int y = ty * p.th + (r / p.tw) % p.th;
-  const int n = tz * p.tn + r / (p.tw * p.th);
+  const int x = o.x0 + r % p.tw;
+  const int y = o.y0 + (r / p.tw) % p.th;
+  const int n = o.z0 + r / (p.tw * p.th);
   if (x >= p.Wo || y >= p.Ho || n >= p.Nimg) return -1;
   return ((long long)n * p.Ho + y) * p.Wo + x;
 }
 
-template <int BN, int STAGES>
 __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ T5Params p) {
-  using SM = T5Smem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B atoms
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t bar_full = base + SM::BAR_OFF;            // STAGES x 8 bytes
-  const uint32_t bar_empty = bar_full + 8 * STAGES;
-  const uint32_t bar_accum = bar_empty + 8 * STAGES;
-  const uint32_t tmem_slot = bar_accum + 8;
-  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(smem + SM::BAR_OFF + 16 * STAGES + 8);
+  const int BN = p.BN, STAGES = p.stages;
+  const uint32_t stage_bytes = T5_A_BYTES + BN * 128;
+  const uint32_t bar_base = base + STAGES * stage_bytes;
+  const uint32_t bar_full = bar_base;                      // STAGES x 8
+  const uint32_t bar_empty = bar_base + 8 * T5_MAX_STAGES;
+  const uint32_t bar_acc_full = bar_empty + 8 * T5_MAX_STAGES;   // 2 x 8
+  const uint32_t bar_acc_empty = bar_acc_full + 16;              // 2 x 8
+  const uint32_t tmem_slot = bar_acc_empty + 16;
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
-  const int n0 = blockIdx.y * BN;
   const int KT = p.K / T5_BK;
 
   if (warp == 0 && lane == 0) {
@@ -175,11 +198,14 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_accum, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(bar_acc_full + 8 * b, 1);
+      mbar_init(bar_acc_empty + 8 * b, T5_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "n"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   tc_fence_before();
@@ -190,129 +216,168 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      // tile origin coordinates
-      int x0 = 0, y0 = 0, z0 = 0;
-      if (p.mode != HI3D_ROWS_PLAIN) {
-        const int tx = tile % p.tiles_x, rest = tile / p.tiles_x;
-        x0 = tx * p.tw;
-        y0 = (rest % p.tiles_y) * p.th;
-        z0 = (rest / p.tiles_y) * p.tn;
-      }
-      int si = 0, so = 0;
-      for (int kt = 0; kt < KT; kt++) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t sA = base + s * SM::STAGE_BYTES;
-        const uint32_t sB = sA + SM::A_BYTES;
-        mbar_expect_tx(bar_full + 8 * s, SM::STAGE_BYTES);
-        const T5Seg sg = p.seg[si];
-        const int c = sg.c_off + so;
-        if (p.mode == HI3D_ROWS_PLAIN)
-          tma_load_2d(sA, &p.amap[sg.map], bar_full + 8 * s, c, tile * T5_BM);
-        else if (p.mode == HI3D_ROWS_CONV2D)
-          tma_load_4d(sA, &p.amap[sg.map], bar_full + 8 * s, c, x0 + sg.dx, y0 + sg.dy, z0);
-        else
-          tma_load_4d(sA, &p.amap[sg.map], bar_full + 8 * s, c, x0, y0 + sg.dt, z0);
-        tma_load_2d(sB, &p.bmap, bar_full + 8 * s, kt * T5_BK, n0);
-        so += T5_BK;
-        if (so >= sg.C) { si++; so = 0; }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const T5Tile o = t5_origin(p, mt);
+        const int n0 = nt * BN;
+        int si = 0, so = 0;
+        for (int kt = 0; kt < KT; kt++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t sA = base + s * stage_bytes;
+          const uint32_t sB = sA + T5_A_BYTES;
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, stage_bytes);
+          const T5Seg sg = p.seg[si];
+          const int c = sg.c_off + so;
+          if (p.mode == HI3D_ROWS_PLAIN)
+            tma_load_2d(sA, &p.amap[sg.map], full, c, mt * T5_BM);
+          else if (p.mode == HI3D_ROWS_CONV2D)
+            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0 + sg.dx, o.y0 + sg.dy, o.z0);
+          else
+            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0, o.y0 + sg.dt, o.z0);
+          tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
+          so += T5_BK;
+          if (so >= sg.C) { si++; so = 0; }
+        }
       }
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, both K-major, N = BN, M = 128
+      // instruction descriptor: D = f32, A = B = f16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T5_BM >> 4) << 24);
-      for (int kt = 0; kt < KT; kt++) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (kt / STAGES) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
+      uint32_t it = 0, at = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, at++) {
+        const uint32_t buf = at & 1;
+        mbar_wait(bar_acc_empty + 8 * buf, ((at >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sA = base + s * SM::STAGE_BYTES;
-        const uint32_t sB = sA + SM::A_BYTES;
-        const uint64_t ad = umma_desc_sw128(sA), bd = umma_desc_sw128(sB);
+        const uint32_t tacc = tmem_base + buf * 256;
+        for (int kt = 0; kt < KT; kt++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sA = base + s * stage_bytes;
+          const uint64_t ad = umma_desc_sw128(sA), bd = umma_desc_sw128(sA + T5_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < T5_BK / 16; k++)   // +32 bytes (2 x 16 B) along K inside the 128-byte swizzle atom
-          tc_mma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
-        tc_commit(bar_empty + 8 * s);            // frees the smem slot when these MMAs retire
+          for (int k = 0; k < T5_BK / 16; k++)   // +32 bytes along K inside the 128-byte swizzle atom
+            tc_mma_f16(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * s);          // frees the smem slot when these MMAs retire
+        }
+        tc_commit(bar_acc_full + 8 * buf);       // accumulator complete
       }
-      tc_commit(bar_accum);                      // accumulator complete
     }
   } else {
-    // ======================= epilogue warps (2..5) =======================
+    // ======================= epilogue warps (2..9) =======================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
+    const int half_sel = (warp - 2) >> 2;        // which of the alternating 32-column chunks
     const bool geglu = (p.act == HI3D_ACT_GEGLU);
-    const int pitch = BN + 8;
-    __half* sC = reinterpret_cast<__half*>(smem);
     const int rl = q * 32 + lane;                // tile-local row == TMEM lane
-    const long long m = t5_row(p, tile, rl);
-    const __half* rbp = nullptr;
-    if (p.rowbias != nullptr && m >= 0) rbp = p.rowbias + (long long)((m / p.rb_div) % p.rb_mod) * p.rb_ld;
+    uint32_t at = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, at++) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const T5Tile o = t5_origin(p, mt);
+      const int n0 = nt * BN;
+      const long long m = t5_row(p, mt, o, rl);
+      const __half* rbp = nullptr;
+      if (p.rowbias != nullptr && m >= 0) rbp = p.rowbias + (long long)((m / p.rb_div) % p.rb_mod) * p.rb_ld;
+      const uint32_t buf = at & 1;
+      mbar_wait(bar_acc_full + 8 * buf, (at >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      for (int c0 = half_sel * 32; c0 < BN; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32(tacc + (uint32_t)c0, v);
+        const int n = n0 + c0;
+        if (m < 0 || n >= p.N) continue;
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const int n = n0 + c0 + j;
-        float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-        if (n < p.N) {
-          if (p.bias != nullptr) { a += __ldg(p.bias + n); b += __ldg(p.bias + n + 1); }
-          if (rbp != nullptr) {
-            const __half2 rb = *reinterpret_cast<const __half2*>(rbp + n);
-            a += __low2float(rb); b += __high2float(rb);
+        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n + j >= p.N) break;
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+          }
+        }
+        if (rbp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n + j >= p.N) break;
+            const Half8 r8 = *reinterpret_cast<const Half8*>(rbp + n + j);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const float2 t = __half22float2(r8.h[k]);
+              f[j + 2 * k] += t.x; f[j + 2 * k + 1] += t.y;
+            }
           }
         }
         if (geglu) {
-          sC[rl * pitch + ((c0 + j) >> 1)] = __float2half_rn(a * gelu_erf_f(b));
+          // 32 accumulator columns = 16 (value, gate) pairs -> 16 outputs = 32 bytes
+          Half8 o8[2];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2)
+            o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(f[2 * j] * gelu_fast(f[2 * j + 1]), f[2 * j + 2] * gelu_fast(f[2 * j + 3]));
+          __half* dst = p.out + m * p.out_ld + (n >> 1);
+          *reinterpret_cast<Half8*>(dst) = o8[0];
+          if (n + 16 < p.N) *reinterpret_cast<Half8*>(dst + 8) = o8[1];
         } else {
-          if (p.act == HI3D_ACT_SILU) { a = silu_f(a); b = silu_f(b); }
-          *reinterpret_cast<uint32_t*>(sC + rl * pitch + c0 + j) = pack_half2(a, b);
-        }
-      }
-    }
-    tc_fence_before();
-    // the 4 epilogue warps synchronise among themselves (named barrier 1, 128 threads)
-    asm volatile("bar.sync 1, 128;\n" ::: "memory");
-    const int et = tid - 64;                     // 0..127
-    const int BNo = geglu ? BN / 2 : BN;
-    const int cpr = BNo / 8;
-    const int Nout = geglu ? p.N / 2 : p.N;
-    const int nout0 = geglu ? n0 / 2 : n0;
-    for (int idx = et; idx < T5_BM * cpr; idx += 128) {
-      const int r = idx / cpr, c = idx - r * cpr;
-      const int nc = nout0 + c * 8;
-      const long long mm = t5_row(p, tile, r);
-      if (mm < 0 || nc >= Nout) continue;
-      Half8 v = *reinterpret_cast<const Half8*>(sC + r * pitch + c * 8);
-      if (p.residual != nullptr) {
-        const Half8 rr = *reinterpret_cast<const Half8*>(p.residual + mm * p.res_ld + nc);
+          if (p.act == HI3D_ACT_SILU) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const float2 x = __half22float2(v.h[k]), y = __half22float2(rr.h[k]);
-          v.h[k] = __floats2half2_rn(x.x + y.x, x.y + y.y);
-        }
-      }
-      if (p.blend_x != nullptr) {
-        const Half8 xx = *reinterpret_cast<const Half8*>(p.blend_x + mm * p.blend_ld + nc);
-        const float al = p.alpha, be = 1.f - p.alpha;
+            for (int j = 0; j < 32; j++) f[j] = silu_f(f[j]);
+          }
+          Half8 o8[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const float2 x = __half22float2(v.h[k]), y = __half22float2(xx.h[k]);
-          v.h[k] = __floats2half2_rn(al * y.x + be * x.x, al * y.y + be * x.y);
+          for (int j = 0; j < 32; j += 2) o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(f[j], f[j + 1]);
+          if (p.residual != nullptr) {
+            const __half* rp = p.residual + m * p.res_ld + n;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              if (n + 8 * c >= p.N) break;
+              const Half8 r8 = *reinterpret_cast<const Half8*>(rp + 8 * c);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const float2 a = __half22float2(o8[c].h[k]), b = __half22float2(r8.h[k]);
+                o8[c].h[k] = __floats2half2_rn(a.x + b.x, a.y + b.y);
+              }
+            }
+          }
+          if (p.blend_x != nullptr) {
+            const __half* xp = p.blend_x + m * p.blend_ld + n;
+            const float al = p.alpha, be = 1.f - p.alpha;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              if (n + 8 * c >= p.N) break;
+              const Half8 x8 = *reinterpret_cast<const Half8*>(xp + 8 * c);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const float2 a = __half22float2(o8[c].h[k]), b = __half22float2(x8.h[k]);
+                o8[c].h[k] = __floats2half2_rn(al * b.x + be * a.x, al * b.y + be * a.y);
+              }
+            }
+          }
+          __half* dst = p.out + m * p.out_ld + n;
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            if (n + 8 * c < p.N) *reinterpret_cast<Half8*>(dst + 8 * c) = o8[c];
         }
       }
-      *reinterpret_cast<Half8*>(p.out + mm * p.out_ld + nc) = v;
+      // this warp is done reading the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -350,21 +415,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 
 static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-template <int BN>
-static int launch_tc5(const T5Params& tp, int tiles, cudaStream_t st) {
-  constexpr int STAGES = (BN == 128) ? 3 : 4;   // BN=128: 97 KB -> two CTAs per SM
-  using SM = T5Smem<BN, STAGES>;
-  auto kern = gemm_tc5_kernel<BN, STAGES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-    if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_done = true;
-  }
-  dim3 grid(tiles, (tp.N + BN - 1) / BN);
-  kern<<<grid, T5_THREADS, SM::TOTAL, st>>>(tp);
-  return check_launch("hi3d_gemm_tc5");
-}
+static int g_sm_count = 0;
 
 }  // namespace hi3d
 
@@ -378,11 +429,13 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   T5Params tp;
   memset(&tp, 0, sizeof(tp));
   tp.M = p->M; tp.N = p->N; tp.K = p->K; tp.mode = p->mode; tp.nseg = p->nseg;
-  int tiles = 0;
-  bool ok = (p->N >= 64);
+  int m_tiles = 0;
+  bool ok = (p->N >= 32) && (p->N % 8 == 0);
+  // the vectorised epilogue needs 16-byte aligned rows / bias
+  ok = ok && ((uintptr_t)p->bias % 16 == 0) && (p->rowbias == nullptr || ((uintptr_t)p->rowbias % 16 == 0 && p->rb_ld % 8 == 0));
   if (p->mode == HI3D_ROWS_PLAIN) {
     tp.tw = 128; tp.th = 1; tp.tn = 1;
-    tiles = (p->M + T5_BM - 1) / T5_BM;
+    m_tiles = (p->M + T5_BM - 1) / T5_BM;
   } else if (p->mode == HI3D_ROWS_CONV2D) {
     ok = ok && p->stride == 1 && p->ups == 0 && p->Ho == p->Hs && p->Wo == p->Ws;
     const int Nimg = ok ? p->M / (p->Ho * p->Wo) : 0;
@@ -394,7 +447,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     ok = ok && pow2(tn) && tw * th * tn == 128 && (Nimg % tn) == 0;
     tp.tw = tw; tp.th = th; tp.tn = tn; tp.Wo = p->Wo; tp.Ho = p->Ho; tp.Nimg = Nimg;
     tp.tiles_x = p->Wo / tw; tp.tiles_y = p->Ho / th;
-    tiles = ok ? tp.tiles_x * tp.tiles_y * (Nimg / tn) : 0;
+    m_tiles = ok ? tp.tiles_x * tp.tiles_y * (Nimg / tn) : 0;
   } else {
     const int HW = p->Ho * p->Wo, T = p->T, B = p->M / (HW * T);
     int ts = 1;
@@ -403,7 +456,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     ok = ok && (T % tf) == 0;
     tp.tw = ts; tp.th = tf; tp.tn = 1; tp.Wo = HW; tp.Ho = T; tp.Nimg = B;
     tp.tiles_x = HW / ts; tp.tiles_y = ok ? T / tf : 1;
-    tiles = ok ? tp.tiles_x * tp.tiles_y * B : 0;
+    m_tiles = ok ? tp.tiles_x * tp.tiles_y * B : 0;
   }
   // distinct A sources -> tensor maps
   const void* srcs[T5_MAX_MAPS];
@@ -423,16 +476,26 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   }
   if (!ok) return hi3d_gemm(p, stream);
 
-  // tile-N: least padded work; ties go to the wider tile, the 64-wide tile pays a 10% penalty
+  // tile-N: multiple of 32 in [32, 256] with the least padded work; ties go to the wider tile
   int BN = 256;
   {
-    double best = 1e30;
-    const int cand[3] = {256, 128, 64};
-    for (int i = 0; i < 3; i++) {
-      double c = (double)((p->N + cand[i] - 1) / cand[i]) * cand[i] * (cand[i] == 64 ? 1.1 : 1.0);
-      if (c < best - 1e-9) { best = c; BN = cand[i]; }
+    long long best = -1;
+    for (int cand = 256; cand >= 32; cand -= 32) {
+      if (p->act == HI3D_ACT_GEGLU && (cand % 64)) continue;     // keep GEGLU output chunks 32-byte aligned
+      const long long cost = (long long)((p->N + cand - 1) / cand) * cand;
+      // prefer >= 128 unless a narrower tile removes more than ~12% padding
+      const long long adj = cand >= 128 ? cost * 8 : cost * 9;
+      if (best < 0 || adj < best) { best = adj; BN = cand; }
     }
   }
+  const int stage_bytes = T5_A_BYTES + BN * 128;
+  int stages = T5_SMEM_BUDGET / stage_bytes;
+  if (stages > T5_MAX_STAGES) stages = T5_MAX_STAGES;
+  if (stages < 2) { return hi3d_gemm(p, stream); }
+  tp.BN = BN; tp.stages = stages;
+  tp.n_tiles = (p->N + BN - 1) / BN;
+  tp.total_tiles = m_tiles * tp.n_tiles;
+
   for (int j = 0; j < nmaps; j++) {
     const cuuint64_t ld = (cuuint64_t)lds[j];
     if (p->mode == HI3D_ROWS_PLAIN) {
@@ -463,7 +526,20 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.rb_ld = p->rb_ld; tp.act = p->act; tp.residual = (const __half*)p->residual; tp.res_ld = p->res_ld;
   tp.blend_x = (const __half*)p->blend_x; tp.blend_ld = p->blend_ld; tp.alpha = p->alpha;
   tp.out = (__half*)p->out; tp.out_ld = p->out_ld;
-  if (BN == 256) return launch_tc5<256>(tp, tiles, st);
-  if (BN == 128) return launch_tc5<128>(tp, tiles, st);
-  return launch_tc5<64>(tp, tiles, st);
+
+  static bool attr_done = false;
+  const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 1024;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+    if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+    attr_done = true;
+  }
+  const int grid = tp.total_tiles < g_sm_count ? tp.total_tiles : g_sm_count;
+  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 1024;
+  gemm_tc5_kernel<<<grid, T5_THREADS, smem, st>>>(tp);
+  return check_launch("hi3d_gemm_tc5");
 }
