@@ -131,20 +131,42 @@ HI3D_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+// The wait names the destination registers as in/out operands so that no use of them can be scheduled above it.
+HI3D_DEVINL void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
-// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): far below the fp16 rounding of the GEGLU output, and a
-// third of the instructions of erff().  gelu(x) = 0.5 x (1 + erf(x / sqrt 2)).
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + MUFU error, far
+// below the fp16 rounding of the GEGLU output): 2 MUFU + ~13 FMA-class instructions per value.
+HI3D_DEVINL float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+HI3D_DEVINL float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 HI3D_DEVINL float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  p *= t;
+  const float ex = ex2_approx(z * z * -1.4426950408889634f);
+  const float e = copysignf(fmaf(-p, ex, 1.0f), x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
 }
 
 struct T5Tile {
@@ -189,6 +211,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
   const uint32_t tmem_slot = bar_acc_empty + 16;
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 32);
+  float* sbias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64);   // [2][256]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KT = p.K / T5_BK;
@@ -285,35 +308,47 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       const __half* rbp = nullptr;
       if (p.rowbias != nullptr && m >= 0) rbp = p.rowbias + (long long)((m / p.rb_div) % p.rb_mod) * p.rb_ld;
       const uint32_t buf = at & 1;
+      // stage this tile's bias slice in shared memory (one float per epilogue thread), then sync the epilogue warps
+      {
+        const int et = tid - 64;
+        const int nb = n0 + et;
+        sbias[buf * 256 + et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      }
+      const float* sb = sbias + buf * 256;
       mbar_wait(bar_acc_full + 8 * buf, (at >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = half_sel * 32; c0 < BN; c0 += 64) {
         uint32_t v[32];
-        tmem_ld32(tacc + (uint32_t)c0, v);
+        tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
         const int n = n0 + c0;
-        if (m < 0 || n >= p.N) continue;
+        const bool live = (m >= 0) && (n < p.N);
+        // issue the row-bias loads while the TMEM read is in flight
+        Half8 rb8[4];
+        if (rbp != nullptr && live) {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (n + 8 * j < p.N) rb8[j] = *reinterpret_cast<const Half8*>(rbp + n + 8 * j);
+        }
+        tmem_ld_wait(v);
+        if (!live) continue;
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n + j >= p.N) break;
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + j);
+          f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
         if (rbp != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j >= p.N) break;
-            const Half8 r8 = *reinterpret_cast<const Half8*>(rbp + n + j);
+          for (int j = 0; j < 4; j++) {
+            if (n + 8 * j >= p.N) break;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              const float2 t = __half22float2(r8.h[k]);
-              f[j + 2 * k] += t.x; f[j + 2 * k + 1] += t.y;
+              const float2 t = __half22float2(rb8[j].h[k]);
+              f[8 * j + 2 * k] += t.x; f[8 * j + 2 * k + 1] += t.y;
             }
           }
         }
@@ -432,7 +467,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   int m_tiles = 0;
   bool ok = (p->N >= 32) && (p->N % 8 == 0);
   // the vectorised epilogue needs 16-byte aligned rows / bias
-  ok = ok && ((uintptr_t)p->bias % 16 == 0) && (p->rowbias == nullptr || ((uintptr_t)p->rowbias % 16 == 0 && p->rb_ld % 8 == 0));
+  ok = ok && (p->rowbias == nullptr || ((uintptr_t)p->rowbias % 16 == 0 && p->rb_ld % 8 == 0));
   if (p->mode == HI3D_ROWS_PLAIN) {
     tp.tw = 128; tp.th = 1; tp.tn = 1;
     m_tiles = (p->M + T5_BM - 1) / T5_BM;
@@ -528,7 +563,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.out = (__half*)p->out; tp.out_ld = p->out_ld;
 
   static bool attr_done = false;
-  const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 1024;
+  const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + 1024;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
     if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
@@ -539,7 +574,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     attr_done = true;
   }
   const int grid = tp.total_tiles < g_sm_count ? tp.total_tiles : g_sm_count;
-  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 1024;
+  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + 1024;
   gemm_tc5_kernel<<<grid, T5_THREADS, smem, st>>>(tp);
   return check_launch("hi3d_gemm_tc5");
 }

@@ -90,15 +90,21 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
                 long long rows_per_cta, int nchunks, const float* __restrict__ ws, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, int apply_silu, __half* __restrict__ y) {
   __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+  __shared__ float stot[GN_GROUPS * 2];
   const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
   const int tid = threadIdx.x, n = blockIdx.y;
+  // combine the per-chunk partials: all loads issued in parallel (one per thread), reduced through shared atomics
+  if (tid < GN_GROUPS * 2) stot[tid] = 0.f;
+  __syncthreads();
+  {
+    const float* w = ws + (long long)n * GN_MAX_CHUNKS * (GN_GROUPS * 2);
+    for (int i = tid; i < nchunks * GN_GROUPS * 2; i += blockDim.x) atomicAdd(&stot[i & (GN_GROUPS * 2 - 1)], w[i]);
+  }
+  __syncthreads();
   if (tid < GN_GROUPS) {
-    double s = 0.0, q = 0.0;
-    const float* w = ws + (long long)n * GN_MAX_CHUNKS * (GN_GROUPS * 2) + 2 * tid;
-    for (int c = 0; c < nchunks; c++) { s += (double)w[c * (GN_GROUPS * 2)]; q += (double)w[c * (GN_GROUPS * 2) + 1]; }
     const double cnt = (double)rows_per_sample * (double)cpg;
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;
+    const double mean = (double)stot[2 * tid] / cnt;
+    double var = (double)stot[2 * tid + 1] / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
     smean[tid] = (float)mean;
     srstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
@@ -257,7 +263,7 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
   int rc = check_launch("hi3d_groupnorm_silu(stats)");
   if (rc) return rc;
   // apply: ~8 row-lane sweeps per CTA, but never fewer CTAs than ~4 waves when the tensor is large enough
-  long long rows_per_cta = (long long)RL * GN_UNROLL * 2;
+  long long rows_per_cta = (long long)RL * GN_UNROLL * 4;
   long long slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
   if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_silu: too many slabs"); return -2; }
   gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
@@ -285,9 +291,9 @@ extern "C" int hi3d_layernorm(const void* x, const void* addvec, int add_div, in
     if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }                             \
     layernorm_kernel<VPL, ROWS><<<(unsigned)blocks, 256, 0, st>>>(xp, ap, add_div, add_mod, M, C, gamma, beta, eps, yp); \
   } while (0)
-  if (CV <= 64) HI3D_LN_LAUNCH(2, 4);
-  else if (CV <= 160) HI3D_LN_LAUNCH(5, 2);
-  else HI3D_LN_LAUNCH(10, 1);
+  if (CV <= 64) HI3D_LN_LAUNCH(2, 8);
+  else if (CV <= 160) HI3D_LN_LAUNCH(5, 4);
+  else HI3D_LN_LAUNCH(10, 2);
 #undef HI3D_LN_LAUNCH
   return check_launch("hi3d_layernorm");
 }
