@@ -1,14 +1,16 @@
 // GroupNorm(32) [+SiLU] and LayerNorm for channels-last fp16 activations.  Statistics in fp32 (final
 // combine in fp64), matching the reference's fp32 GroupNorm32 / autocast-fp32 LayerNorm.
-// Both are pure HBM streams: every thread owns one fixed 16-byte channel column, keeps its per-channel
-// constants in registers and walks rows with several independent 16-byte loads in flight.
+// Both are pure HBM streams: every thread owns fixed 16-byte channel columns, keeps its per-channel
+// constants in registers and walks rows with several independent 16-byte loads in flight; grids are sized to a
+// few full waves of the 148 SMs.
 #include "common.cuh"
 
 namespace hi3d {
 
-constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_MAX_CHUNKS = 512;
 constexpr int GN_GROUPS = 32;
 constexpr int GN_UNROLL = 4;
+constexpr int GN_TARGET_CTAS = 148 * 4 * 4;   // ~4 waves at 4 CTAs/SM
 
 HI3D_DEVINL Half8 ld_stream(const __half* p) {
   Half8 v;
@@ -83,31 +85,42 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   if (tid < GN_GROUPS * 2) ws[((long long)n * GN_MAX_CHUNKS + chunk) * (GN_GROUPS * 2) + tid] = sg[tid];
 }
 
-// ---- pass 2: y = [silu]((x - mean) * rstd * gamma + beta) ------------------------------------------
-// grid (row_slabs, n_samples), blockDim = RL * CV.
-__global__ void __launch_bounds__(512)
-gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
-                long long rows_per_cta, int nchunks, const float* __restrict__ ws, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, int apply_silu, __half* __restrict__ y) {
-  __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+// ---- pass 1b: combine the chunk partials of one sample into (mean, rstd) per group -------------------------
+// grid (n_samples), 256 threads; result at fin[n][32][2].
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ ws, int nchunks, long long rows_per_sample, int cpg, float eps,
+                   float* __restrict__ fin) {
   __shared__ float stot[GN_GROUPS * 2];
-  const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
-  const int tid = threadIdx.x, n = blockIdx.y;
-  // combine the per-chunk partials: all loads issued in parallel (one per thread), reduced through shared atomics
+  const int tid = threadIdx.x, n = blockIdx.x;
   if (tid < GN_GROUPS * 2) stot[tid] = 0.f;
   __syncthreads();
-  {
-    const float* w = ws + (long long)n * GN_MAX_CHUNKS * (GN_GROUPS * 2);
-    for (int i = tid; i < nchunks * GN_GROUPS * 2; i += blockDim.x) atomicAdd(&stot[i & (GN_GROUPS * 2 - 1)], w[i]);
-  }
+  const float* w = ws + (long long)n * GN_MAX_CHUNKS * (GN_GROUPS * 2);
+  float acc = 0.f;                                   // thread owns value index tid % 64, chunks tid/64, +4, ...
+  for (int c = tid >> 6; c < nchunks; c += 4) acc += w[c * (GN_GROUPS * 2) + (tid & 63)];
+  atomicAdd(&stot[tid & 63], acc);
   __syncthreads();
   if (tid < GN_GROUPS) {
     const double cnt = (double)rows_per_sample * (double)cpg;
     const double mean = (double)stot[2 * tid] / cnt;
     double var = (double)stot[2 * tid + 1] / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    smean[tid] = (float)mean;
-    srstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+    fin[(long long)n * (GN_GROUPS * 2) + 2 * tid] = (float)mean;
+    fin[(long long)n * (GN_GROUPS * 2) + 2 * tid + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// ---- pass 2: y = [silu]((x - mean) * rstd * gamma + beta) ------------------------------------------
+// grid (row_slabs, n_samples), blockDim = RL * CV.
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
+                long long rows_per_cta, const float* __restrict__ fin, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int apply_silu, __half* __restrict__ y) {
+  __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+  const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
+  const int tid = threadIdx.x, n = blockIdx.y;
+  if (tid < GN_GROUPS) {
+    smean[tid] = fin[(long long)n * (GN_GROUPS * 2) + 2 * tid];
+    srstd[tid] = fin[(long long)n * (GN_GROUPS * 2) + 2 * tid + 1];
   }
   __syncthreads();
   const int cv = tid % CV, rl = tid / CV, RL = blockDim.x / CV;
@@ -150,78 +163,138 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   for (; r < r1; r += RL) *reinterpret_cast<Half8*>(yb + r * C) = xform(ld_stream(base + r * ld));
 }
 
-// ---- LayerNorm: one warp per LN_ROWS rows, rows kept in registers --------------------------------------------
-template <int VPL, int ROWS>
+// ---- LayerNorm: LPR lanes per row (32/LPR rows per warp pass), VPL 16-byte vectors per lane ------------------
+// C = 8 * VPL * LPR exactly (C = 320 -> VPL 5, LPR 8; 640 -> 5 x 16; 1280 -> 5 x 32; 64 -> 1 x 8; 2560 -> 10 x 32).
+template <int VPL, int LPR>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ addvec, int add_div, int add_mod, long long M,
                  int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  __half* __restrict__ y) {
+  constexpr int RPW = 32 / LPR;                      // rows per warp pass
   const int lane = threadIdx.x & 31;
-  const long long m0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS;
-  if (m0 >= M) return;
-  const int CV = C >> 3;
-  Half8 raw[ROWS][VPL];
+  const int sub = lane % LPR, rsel = lane / LPR;
+  const long long wrow0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
+  const long long m = wrow0 + rsel;
+  const bool live = m < M;
+  const float invC = 1.f / (float)C;
+  Half8 raw[VPL];
+  if (live) {
 #pragma unroll
-  for (int r = 0; r < ROWS; r++)
-#pragma unroll
-    for (int i = 0; i < VPL; i++) {
-      const int cv = lane + 32 * i;
-      if (cv < CV && m0 + r < M) raw[r][i] = ld_stream(x + (m0 + r) * C + cv * 8);
-    }
-#pragma unroll
-  for (int r = 0; r < ROWS; r++) {
-    const long long m = m0 + r;
-    if (m >= M) break;
+    for (int i = 0; i < VPL; i++) raw[i] = ld_stream(x + m * C + (sub + LPR * i) * 8);
+  }
+  float v[VPL][8];
+  float sum = 0.f;
+  if (live) {
     const __half* av = addvec ? addvec + (long long)((m / add_div) % add_mod) * C : nullptr;
-    float v[VPL][8];
-    float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; i++) {
-      const int cv = lane + 32 * i;
-      if (cv < CV) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(raw[i].h[k]);
+        v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+      }
+      if (av) {
+        const Half8 a = *reinterpret_cast<const Half8*>(av + (sub + LPR * i) * 8);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const float2 f = __half22float2(raw[r][i].h[k]);
-          v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+          const float2 f = __half22float2(a.h[k]);
+          v[i][2 * k] += f.x; v[i][2 * k + 1] += f.y;
         }
-        if (av) {
-          const Half8 a = *reinterpret_cast<const Half8*>(av + cv * 8);
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const float2 f = __half22float2(a.h[k]);
-            v[i][2 * k] += f.x; v[i][2 * k + 1] += f.y;
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; e++) sum += v[i][e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; e++) v[i][e] = 0.f;
       }
+#pragma unroll
+      for (int e = 0; e < 8; e++) sum += v[i][e];
     }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPL; i++)
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[i][e] = 0.f;
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * invC;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; i++)
+#pragma unroll
+    for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; sq += d * d; }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * invC + eps);
+  if (live) {
 #pragma unroll
     for (int i = 0; i < VPL; i++) {
-      if (lane + 32 * i < CV) {
+      const int c0 = (sub + LPR * i) * 8;
+      Half8 o;
 #pragma unroll
-        for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; sq += d * d; }
+      for (int k = 0; k < 4; k++) {
+        const float2 gm = *reinterpret_cast<const float2*>(gamma + c0 + 2 * k);
+        const float2 bt = *reinterpret_cast<const float2*>(beta + c0 + 2 * k);
+        o.h[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * gm.x + bt.x, (v[i][2 * k + 1] - mean) * rstd * gm.y + bt.y);
       }
+      *reinterpret_cast<Half8*>(y + m * C + c0) = o;
     }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  }
+}
+
+// generic fallback: one warp per row, up to 10 vectors per lane with masking (any C % 8 == 0, C <= 2560)
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_generic_kernel(const __half* __restrict__ x, const __half* __restrict__ addvec, int add_div, int add_mod,
+                         long long M, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         __half* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int CV = C >> 3;
+  const __half* av = addvec ? addvec + (long long)((m / add_div) % add_mod) * C : nullptr;
+  float v[VPL][8];
+  float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; i++) {
-      const int cv = lane + 32 * i;
-      if (cv < CV) {
-        Half8 o;
+  for (int i = 0; i < VPL; i++) {
+    const int cv = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[i][e] = 0.f;
+    if (cv < CV) {
+      const Half8 h = ld_stream(x + m * C + cv * 8);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(h.h[k]);
+        v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
+      }
+      if (av) {
+        const Half8 a = *reinterpret_cast<const Half8*>(av + cv * 8);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const int c = cv * 8 + 2 * k;
-          const float2 gm = *reinterpret_cast<const float2*>(gamma + c), bt = *reinterpret_cast<const float2*>(beta + c);
-          o.h[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * gm.x + bt.x, (v[i][2 * k + 1] - mean) * rstd * gm.y + bt.y);
+          const float2 f = __half22float2(a.h[k]);
+          v[i][2 * k] += f.x; v[i][2 * k + 1] += f.y;
         }
-        *reinterpret_cast<Half8*>(y + m * C + cv * 8) = o;
       }
+#pragma unroll
+      for (int e = 0; e < 8; e++) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; i++)
+    if (lane + 32 * i < CV) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) { const float d = v[i][e] - mean; sq += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const int cv = lane + 32 * i;
+    if (cv < CV) {
+      Half8 o;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = cv * 8 + 2 * k;
+        o.h[k] = __floats2half2_rn((v[i][2 * k] - mean) * rstd * gamma[c] + beta[c],
+                                   (v[i][2 * k + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+      }
+      *reinterpret_cast<Half8*>(y + m * C + cv * 8) = o;
     }
   }
 }
@@ -231,7 +304,7 @@ layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ addvec
 using namespace hi3d;
 
 extern "C" int64_t hi3d_groupnorm_ws_floats(int n_samples) {
-  return (int64_t)n_samples * GN_MAX_CHUNKS * GN_GROUPS * 2;
+  return (int64_t)n_samples * (GN_MAX_CHUNKS + 1) * GN_GROUPS * 2;     // chunk partials + final (mean, rstd)
 }
 
 extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples,
@@ -250,25 +323,34 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
   const int CV = C / 8;
   const int threads = (512 / CV) * CV;
   const int RL = threads / CV;
-  // enough CTAs for a few waves; every chunk at least GN_UNROLL row-lane sweeps deep
-  long long chunks = (592 + n_samples - 1) / n_samples;
-  const long long max_by_rows = (rows_per_sample + (long long)RL * GN_UNROLL - 1) / ((long long)RL * GN_UNROLL);
+  const long long min_rows = (long long)RL * GN_UNROLL;     // one unrolled sweep per thread at least
+  // ---- stats: ~4 waves of CTAs, bounded by the workspace layout and by a minimum of work per CTA
+  long long chunks = (GN_TARGET_CTAS + n_samples - 1) / n_samples;
+  const long long max_by_rows = (rows_per_sample + min_rows - 1) / min_rows;
   if (chunks > max_by_rows) chunks = max_by_rows;
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
   if (chunks < 1) chunks = 1;
   long long rpc = (rows_per_sample + chunks - 1) / chunks;
+  rpc = (rpc + RL - 1) / RL * RL;
   chunks = (rows_per_sample + rpc - 1) / rpc;
   gn_stats_kernel<<<dim3((unsigned)chunks, n_samples), threads, 0, st>>>((const __half*)x1, C1, (const __half*)x2, C2,
                                                                         rows_per_sample, rpc, ws);
   int rc = check_launch("hi3d_groupnorm_silu(stats)");
   if (rc) return rc;
-  // apply: ~8 row-lane sweeps per CTA, but never fewer CTAs than ~4 waves when the tensor is large enough
-  long long rows_per_cta = (long long)RL * GN_UNROLL * 4;
-  long long slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
+  float* fin = ws + (long long)n_samples * GN_MAX_CHUNKS * GN_GROUPS * 2;
+  gn_finalize_kernel<<<n_samples, 256, 0, st>>>(ws, (int)chunks, rows_per_sample, C / GN_GROUPS, eps, fin);
+  rc = check_launch("hi3d_groupnorm_silu(finalize)");
+  if (rc) return rc;
+  // ---- apply: same sizing rule (each CTA also re-reduces `chunks` x 64 partials, a few KB)
+  long long slabs = (GN_TARGET_CTAS + n_samples - 1) / n_samples;
+  if (slabs > max_by_rows) slabs = max_by_rows;
+  if (slabs < 1) slabs = 1;
+  long long rows_per_cta = (rows_per_sample + slabs - 1) / slabs;
+  rows_per_cta = (rows_per_cta + RL - 1) / RL * RL;
+  slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
   if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_silu: too many slabs"); return -2; }
   gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
-      (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, (int)chunks, ws, gamma, beta, eps,
-      apply_silu, (__half*)y);
+      (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, fin, gamma, beta, apply_silu, (__half*)y);
   return check_launch("hi3d_groupnorm_silu(apply)");
 }
 
@@ -285,15 +367,31 @@ extern "C" int hi3d_layernorm(const void* x, const void* addvec, int add_div, in
   const __half* xp = (const __half*)x;
   const __half* ap = (const __half*)addvec;
   __half* yp = (__half*)y;
-#define HI3D_LN_LAUNCH(VPL, ROWS)                                                                                   \
-  do {                                                                                                              \
-    const long long blocks = (M + 8 * ROWS - 1) / (8 * ROWS);                                                       \
-    if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }                             \
-    layernorm_kernel<VPL, ROWS><<<(unsigned)blocks, 256, 0, st>>>(xp, ap, add_div, add_mod, M, C, gamma, beta, eps, yp); \
+#define HI3D_LN_LAUNCH(VPL, LPR)                                                                                        \
+  do {                                                                                                                  \
+    const long long rows_per_cta = 8 * (32 / LPR);                                                                      \
+    const long long blocks = (M + rows_per_cta - 1) / rows_per_cta;                                                     \
+    if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }                                 \
+    layernorm_kernel<VPL, LPR><<<(unsigned)blocks, 256, 0, st>>>(xp, ap, add_div, add_mod, M, C, gamma, beta, eps, yp);  \
   } while (0)
-  if (CV <= 64) HI3D_LN_LAUNCH(2, 8);
-  else if (CV <= 160) HI3D_LN_LAUNCH(5, 4);
-  else HI3D_LN_LAUNCH(10, 2);
+#define HI3D_LN_GENERIC(VPL)                                                                                             \
+  do {                                                                                                                  \
+    const long long blocks = (M + 7) / 8;                                                                               \
+    if (blocks > 2147483647LL) { set_error("hi3d_layernorm: M too large"); return -2; }                                 \
+    layernorm_generic_kernel<VPL><<<(unsigned)blocks, 256, 0, st>>>(xp, ap, add_div, add_mod, M, C, gamma, beta, eps, yp); \
+  } while (0)
+  if (CV == 40) HI3D_LN_LAUNCH(5, 8);            // C = 320
+  else if (CV == 80) HI3D_LN_LAUNCH(5, 16);      // C = 640
+  else if (CV == 160) HI3D_LN_LAUNCH(5, 32);     // C = 1280
+  else if (CV == 8) HI3D_LN_LAUNCH(1, 8);        // C = 64
+  else if (CV == 16) HI3D_LN_LAUNCH(2, 8);       // C = 128
+  else if (CV == 32) HI3D_LN_LAUNCH(2, 16);      // C = 256
+  else if (CV == 64) HI3D_LN_LAUNCH(2, 32);      // C = 512
+  else if (CV == 320) HI3D_LN_LAUNCH(10, 32);    // C = 2560
+  else if (CV <= 64) HI3D_LN_GENERIC(2);
+  else if (CV <= 160) HI3D_LN_GENERIC(5);
+  else HI3D_LN_GENERIC(10);
 #undef HI3D_LN_LAUNCH
+#undef HI3D_LN_GENERIC
   return check_launch("hi3d_layernorm");
 }

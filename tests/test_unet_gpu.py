@@ -44,10 +44,12 @@ def inputs(N, cin, hw, adm, T, seed=0):
     return x, ctx, y, t
 
 
-@pytest.mark.parametrize("mc,T,hw", [(64, 4, 16), (64, 16, 8), (128, 8, 16)])
-def test_small_unet_vs_oracle(mc, T, hw):
+@pytest.mark.parametrize("engine", ["mma", "tc5"])
+@pytest.mark.parametrize("mc,T,hw", [(64, 4, 16), (64, 16, 8), (128, 8, 16), (64, 16, 32)])
+def test_small_unet_vs_oracle(mc, T, hw, engine):
     kw = dict(KW_S1, model_channels=mc)
     net, sd = build(kw)
+    net.set_engine(engine)
     N = 2 * T
     x, ctx, y, t = inputs(N, 8, hw, 768, T)
     out = net(x, timesteps=t, context=ctx, y=y, num_video_frames=T, image_only_indicator=torch.zeros(2, T).cuda())
@@ -58,9 +60,11 @@ def test_small_unet_vs_oracle(mc, T, hw):
     assert frac < 1e-3 and mx < 5e-2
 
 
-def test_full_width_unet_vs_oracle_small_latents():
+@pytest.mark.parametrize("engine", ["mma", "tc5"])
+def test_full_width_unet_vs_oracle_small_latents(engine):
     """Stage-1 architecture at full width (1.52 B params), 16x16 latents, T=16 (CFG batch 32)."""
     net, sd = build(KW_S1)
+    net.set_engine(engine)
     T, N = 16, 32
     x, ctx, y, t = inputs(N, 8, 16, 768, T, seed=3)
     out = net(x, timesteps=t, context=ctx, y=y, num_video_frames=T)
