@@ -1,0 +1,266 @@
+// Spatial self-attention core (head dim 64) on tcgen05 / TMEM / TMA.
+//
+// One CTA = 128 queries of one (image, head).  Per 128-key tile:
+//   S = Q K^T        tcgen05.mma, A = Q (smem, K-major), B = K tile (smem, K-major)      -> TMEM S[b]  (128 fp32 cols)
+//   softmax          4 warps, one thread per query row: two passes over its TMEM row (max, then exp2 / sum),
+//                    P written back as packed fp16 into the first 64 columns of the same S[b] region
+//   O_j = P V        tcgen05.mma, A = P (TMEM), B = V tile (smem, MN-major: rows = keys)    -> TMEM O[b]   (64 fp32 cols)
+//   O   = O * corr_j + O_j   in the row-owner's registers (fp32), so the accumulator never needs an in-TMEM rescale
+// S and O are double buffered: Q K^T of tile j+1 is issued before the softmax of tile j has finished.
+// Warp roles (192 threads): warp 0 = TMA producer (Q once, K/V ring), warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = softmax / accumulate / store.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc5.cuh"
+
+namespace hi3d {
+
+constexpr int FA_BM = 128;           // queries per CTA
+constexpr int FA_BN = 128;           // keys per tile
+constexpr int FA_STAGES = 3;         // K/V ring depth
+constexpr int FA_THREADS = 192;
+constexpr int FA_TILE_BYTES = 128 * 128;                 // 128 rows x 64 fp16
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256 + 1024;
+
+HI3D_DEVINL float ex2_approx_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+struct FaParams {
+  CUtensorMap qkv_map;     // 2-D view of the packed [rows, 3C] matrix, box {64, 128}
+  int L, C, heads;
+  float scale_log2;
+  __half* out;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sQ = base;
+  const uint32_t sKV = base + FA_TILE_BYTES;                  // stage s: K at sKV + s*2T, V at + T
+  const uint32_t bar0 = base + FA_TILE_BYTES * (1 + 2 * FA_STAGES);
+  const uint32_t bar_q = bar0;                                // Q landed
+  const uint32_t bar_kv_full = bar0 + 8;                      // [STAGES]
+  const uint32_t bar_kv_empty = bar_kv_full + 8 * FA_STAGES;  // [STAGES]
+  const uint32_t bar_s_full = bar_kv_empty + 8 * FA_STAGES;   // [2]  S[b] written by the MMA
+  const uint32_t bar_p_full = bar_s_full + 16;                // [2]  P[b] written by the softmax warps
+  const uint32_t bar_o_full = bar_p_full + 16;                // [2]  O[b] written by the MMA
+  const uint32_t bar_o_empty = bar_o_full + 16;               // [2]  O[b] consumed by the softmax warps
+  const uint32_t tmem_slot = bar_o_empty + 16;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * FA_BM;
+  const int h = blockIdx.y;
+  const int row0 = blockIdx.z * p.L;          // first token row of this image
+  const int nkv = p.L / FA_BN;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < FA_STAGES; s++) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(bar_s_full + 8 * b, 1);
+      mbar_init(bar_p_full + 8 * b, 4);
+      mbar_init(bar_o_full + 8 * b, 1);
+      mbar_init(bar_o_empty + 8 * b, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  // TMEM columns: S[0] = [0,128), S[1] = [128,256), O[0] = [256,320), O[1] = [320,384)
+  const uint32_t tS0 = tmem_base, tO0 = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, FA_TILE_BYTES);
+      tma_load_2d(sQ, &p.qkv_map, bar_q, h * 64, row0 + q0);
+      for (int j = 0; j < nkv; j++) {
+        const int s = j % FA_STAGES;
+        mbar_wait(bar_kv_empty + 8 * s, ((j / FA_STAGES) & 1) ^ 1);
+        const uint32_t full = bar_kv_full + 8 * s;
+        mbar_expect_tx(full, 2 * FA_TILE_BYTES);
+        tma_load_2d(sKV + s * 2 * FA_TILE_BYTES, &p.qkv_map, full, p.C + h * 64, row0 + j * FA_BN);
+        tma_load_2d(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES, &p.qkv_map, full, 2 * p.C + h * 64, row0 + j * FA_BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // S = Q K^T : M 128, N 128, A/B K-major.   O = P V : M 128, N 64, A from TMEM, B MN-major (bit 16).
+      const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+      const uint64_t qd = umma_desc_sw128(sQ);
+      mbar_wait(bar_q, 0);
+      auto issue_qk = [&](int j) {
+        const int s = j % FA_STAGES;
+        mbar_wait(bar_kv_full + 8 * s, (j / FA_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t kd = umma_desc_sw128(sKV + s * 2 * FA_TILE_BYTES);
+        const uint32_t tS = tS0 + (j & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < 4; k++) tc_mma_f16(tS, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
+        tc_commit(bar_s_full + 8 * (j & 1));
+      };
+      issue_qk(0);
+      for (int j = 0; j < nkv; j++) {
+        if (j + 1 < nkv) issue_qk(j + 1);           // overlaps the softmax of tile j
+        const int b = j & 1, s = j % FA_STAGES;
+        mbar_wait(bar_p_full + 8 * b, (j >> 1) & 1);           // P[b] of tile j is in TMEM
+        mbar_wait(bar_o_empty + 8 * b, ((j >> 1) & 1) ^ 1);    // O[b] of tile j-2 has been consumed
+        tc_fence_after();
+        const uint64_t vd = umma_desc_sw128_mn(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES);
+        const uint32_t tP = tS0 + b * 128, tO = tO0 + b * 64;
+#pragma unroll
+        for (int k = 0; k < 8; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
+          tc_mma_f16_ts(tO, tP + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, k ? 1u : 0u);
+        tc_commit(bar_o_full + 8 * b);
+        tc_commit(bar_kv_empty + 8 * s);
+      }
+    }
+  } else {
+    // ======================= softmax / accumulate warps =======================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // query row within the tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c = p.scale_log2;
+    float oacc[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) oacc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    for (int j = 0; j < nkv; j++) {
+      const int b = j & 1;
+      mbar_wait(bar_s_full + 8 * b, (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tS = tS0 + b * 128 + lane_off;
+      // pass 1: row max
+      float mx = m_run;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc++) {
+        uint32_t v[32];
+        tmem_ld32(tS + 32 * cc, v);
+        tmem_ld_wait(v);
+#pragma unroll
+        for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float corr = exp2f((m_run - mx) * c);       // m_run = -inf on the first tile -> 0
+      const float moff = mx * c;
+      m_run = mx;
+      // pass 2: P = exp2(S*c - m*c), row sum, packed fp16 back into the same TMEM region
+      float rs = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc++) {
+        uint32_t v[32];
+        tmem_ld32(tS + 32 * cc, v);
+        tmem_ld_wait(v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx_ftz(fmaf(__uint_as_float(v[i]), c, -moff));
+          const float p1 = ex2_approx_ftz(fmaf(__uint_as_float(v[i + 1]), c, -moff));
+          rs += p0 + p1;
+          pk[i >> 1] = pack_half2(p0, p1);
+        }
+        tmem_st16(tS + 16 * cc, pk);
+      }
+      tmem_st_wait();
+      l_run = l_run * corr + rs;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full + 8 * b);
+      // fold in the previous tile's P V while the tensor core works on this one
+      if (j > 0) {
+        const int pb = (j - 1) & 1;
+        mbar_wait(bar_o_full + 8 * pb, ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tO = tO0 + pb * 64 + lane_off;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          uint32_t v[32];
+          tmem_ld32(tO + 32 * cc, v);
+          tmem_ld_wait(v);
+#pragma unroll
+          for (int i = 0; i < 32; i++) oacc[32 * cc + i] = fmaf(oacc[32 * cc + i], corr_prev, __uint_as_float(v[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_o_empty + 8 * pb);
+      }
+      corr_prev = corr;
+    }
+    {
+      const int pb = (nkv - 1) & 1;
+      mbar_wait(bar_o_full + 8 * pb, ((nkv - 1) >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tO = tO0 + pb * 64 + lane_off;
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        uint32_t v[32];
+        tmem_ld32(tO + 32 * cc, v);
+        tmem_ld_wait(v);
+#pragma unroll
+        for (int i = 0; i < 32; i++) oacc[32 * cc + i] = fmaf(oacc[32 * cc + i], corr_prev, __uint_as_float(v[i]));
+      }
+    }
+    const float inv = 1.f / l_run;
+    __half* dst = p.out + (long long)(row0 + q0 + r) * p.C + h * 64;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+      Half8 o8;
+#pragma unroll
+      for (int k = 0; k < 4; k++) o8.h[k] = __floats2half2_rn(oacc[i + 2 * k] * inv, oacc[i + 2 * k + 1] * inv);
+      *reinterpret_cast<Half8*>(dst + i) = o8;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace hi3d
+
+using namespace hi3d;
+
+extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream) {
+  if (!qkv || !out || n_img <= 0 || L <= 0 || heads <= 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) {
+    set_error("hi3d_attention_d64_tc5: bad arguments (n_img=%d L=%d heads=%d)", n_img, L, heads);
+    return -2;
+  }
+  if ((L % FA_BN) || heads > 65535 || n_img > 65535)      // ragged / tiny sequences: mma.sync kernel (same results)
+    return hi3d_attention_d64(qkv, n_img, L, heads, scale, out, stream);
+  FaParams fp;
+  memset(&fp, 0, sizeof(fp));
+  const int C = heads * 64;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)n_img * (cuuint64_t)L};
+    cuuint64_t str[1] = {(cuuint64_t)(3 * C) * 2};
+    cuuint32_t box[2] = {64, 128};
+    if (encode_map(&fp.qkv_map, qkv, 2, dims, str, box)) return -1;
+  }
+  fp.L = L; fp.C = C; fp.heads = heads;
+  fp.scale_log2 = scale * 1.4426950408889634f;
+  fp.out = (__half*)out;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(fmha_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
+    if (e != cudaSuccess) { set_error("hi3d_attention_d64_tc5: %s", cudaGetErrorString(e)); return -1; }
+    attr_done = true;
+  }
+  dim3 grid(L / FA_BM, heads, n_img);
+  fmha_tc5_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(fp);
+  return check_launch("hi3d_attention_d64_tc5");
+}

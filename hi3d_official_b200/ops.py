@@ -151,10 +151,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch
                                     beta.data_ptr(), eps, y.data_ptr(), _stream()), "hi3d_layernorm")
 
 
-def attention_d64(qkv: torch.Tensor, n_img: int, L: int, heads: int, out: torch.Tensor, scale: float = 0.125):
+def attention_d64(qkv: torch.Tensor, n_img: int, L: int, heads: int, out: torch.Tensor, scale: float = 0.125,
+                  engine: str = "mma"):
     _chk16(qkv, "qkv"); _chk16(out, "out")
-    N.check(N.load().hi3d_attention_d64(qkv.data_ptr(), n_img, L, heads, scale, out.data_ptr(), _stream()),
-            "hi3d_attention_d64")
+    fn = N.load().hi3d_attention_d64_tc5 if engine == "tc5" else N.load().hi3d_attention_d64
+    N.check(fn(qkv.data_ptr(), n_img, L, heads, scale, out.data_ptr(), _stream()), "hi3d_attention_d64")
 
 
 def temporal_attention_d64(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, out: torch.Tensor,

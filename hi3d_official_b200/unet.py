@@ -19,6 +19,7 @@ Algebraic folds relative to the reference graph (all exact in real arithmetic; S
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -248,6 +249,7 @@ class _Plan:
         self.P = net._pack()
         self.dev = net.device
         self.engine = net.engine
+        self.attn_engine = os.environ.get("HI3D_ATTN_ENGINE", net.engine)
         self.arena = Arena(self.dev)
         self.steps: List = []          # main per-step launch list (built lazily as (kind, builder) then baked)
         self._build: List = []         # deferred builders, run after the arena is materialised
@@ -490,7 +492,7 @@ class _Plan:
             # ---- spatial BasicTransformerBlock (attention.py:551-572)
             self._ln(bl, tok, P[qs + "norm1"], ln, M)
             self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qs + "qkv"], qkv, M)
-            self._call(bl, lambda: ops.attention_d64(qkv.t, N, HW, heads, att.t), kind="spatial_attention",
+            self._call(bl, lambda: ops.attention_d64(qkv.t, N, HW, heads, att.t, engine=self.attn_engine), kind="spatial_attention",
                        flops=4.0 * N * HW * HW * C, bytes=8.0 * M * C)
             self.flops += 4.0 * N * HW * HW * C
             self._gemm(bl, lambda: [ops.SegSpec(att.t)], P[qs + "to_out"][0], t1, M, bias=P[qs + "to_out"][1],

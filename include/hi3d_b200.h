@@ -120,6 +120,9 @@ int hi3d_layernorm(const void* x, const void* addvec, int add_div, int add_mod, 
  * qkv: fp16 [n_img*L, 3*C] with q | k | v column blocks, heads contiguous (C = heads*64); out fp16 [n_img*L, C].
  * Replaces F.scaled_dot_product_attention / xformers.memory_efficient_attention at attention.py:334,427-439. */
 int hi3d_attention_d64(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream);
+/* same contract on tcgen05 / TMEM / TMA (S and P*V accumulators in tensor memory, P fed back from TMEM);
+ * sequences that are not a multiple of 128 keys are forwarded to hi3d_attention_d64. */
+int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream);
 
 /* Temporal self-attention core over the frame axis (T <= 16), head dim 64, for every (clip, pixel, head):
  * token row of (b, t, s) is (b*T + t)*S + s -- the "(b t) s c -> (b s) t c" rearrange of

@@ -1,0 +1,37 @@
+"""tcgen05 / TMEM spatial attention (hi3d_attention_d64_tc5) against PyTorch fp32 softmax(QK^T/8)V and against the
+mma.sync kernel, incl. the ragged-length forwarding path."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from hi3d_official_b200 import ops  # noqa: E402
+from test_kernels_gpu import DEV, H, close, rnd  # noqa: E402
+
+
+def ref_attn(qkv, n_img, L, heads):
+    C = heads * 64
+    q, k, v = (t.view(n_img, L, heads, 64).transpose(1, 2).float() for t in qkv.view(n_img * L, 3, C).unbind(1))
+    return torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v
+
+
+@pytest.mark.parametrize("n_img,L,heads,scale", [(1, 128, 1, 1.0), (2, 256, 2, 1.0), (3, 1024, 5, 1.0), (1, 4096, 2, 1.0),
+                                                 (2, 1024, 3, 3.0), (1, 384, 1, 0.3)])
+def test_attention_tc5(n_img, L, heads, scale):
+    C = heads * 64
+    qkv = (rnd(n_img * L, 3 * C) * scale).to(H)
+    out = torch.zeros(n_img * L, C, dtype=H, device=DEV)
+    ops.attention_d64(qkv, n_img, L, heads, out, engine="tc5")
+    ref = ref_attn(qkv, n_img, L, heads)
+    close(out.view(n_img, L, heads, 64).transpose(1, 2), ref, atol=2e-3, name="fmha tc5")
+    out2 = torch.zeros_like(out)
+    ops.attention_d64(qkv, n_img, L, heads, out2, engine="mma")
+    close(out, out2, atol=2e-3, name="tc5 vs mma")
+
+
+def test_attention_tc5_ragged_forwards():
+    n_img, L, heads = 2, 100, 2
+    qkv = rnd(n_img * L, 3 * heads * 64).to(H)
+    out = torch.zeros(n_img * L, heads * 64, dtype=H, device=DEV)
+    ops.attention_d64(qkv, n_img, L, heads, out, engine="tc5")
+    close(out.view(n_img, L, heads, 64).transpose(1, 2), ref_attn(qkv, n_img, L, heads), atol=2e-3, name="ragged")
