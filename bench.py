@@ -218,7 +218,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--stage", type=int, default=1, choices=(1, 2))
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
-    ap.add_argument("--engine", default=os.environ.get("HI3D_ENGINE", "mma"), choices=("mma", "tc5"))
+    ap.add_argument("--engine", default=os.environ.get("HI3D_ENGINE", "tc5"), choices=("mma", "tc5"))
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--cpu-latent", type=int, default=8, help="latent size of the bounded CPU sample")
     args = ap.parse_args()

@@ -98,7 +98,7 @@ class VideoUNet(nn.Module):
             self.add_module(k, m)
         self._packed: Optional[dict] = None
         self._plans: Dict[tuple, "_Plan"] = {}
-        self.engine = "mma"
+        self.engine = os.environ.get("HI3D_ENGINE", "tc5")     # "tc5" = tcgen05/TMEM/TMA engine, "mma" = mma.sync engine
 
     # ---- parameter lifecycle ---------------------------------------------------------------------------
     def _invalidate(self):

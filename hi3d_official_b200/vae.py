@@ -10,6 +10,8 @@ accumulation (the reference runs the first stage in pure fp16: `disable_first_st
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -217,7 +219,7 @@ class AutoencoderKL(nn.Module):
             roots[root].put(rest, nn.Parameter(torch.empty(shp), requires_grad=False))
         self._packed = None
         self._plans: Dict[tuple, _VAEPlan] = {}
-        self.engine = "mma"
+        self.engine = os.environ.get("HI3D_ENGINE", "tc5")     # "tc5" = tcgen05/TMEM/TMA engine, "mma" = mma.sync engine
         self.max_batch_size = ignored.get("max_batch_size", None)
 
     # -- lifecycle ----------------------------------------------------------------------------------------------------

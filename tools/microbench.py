@@ -108,8 +108,9 @@ def main():
             L, M, heads = h * h, N * h * h, C // 64
             qkv = rnd(M, 3 * C)
             out = torch.empty(M, C, dtype=H, device=DEV)
-            report(f"spatial attention L={L} heads={heads}", timeit(lambda: ops.attention_d64(qkv, N, L, heads, out), once=args.once),
-                   4.0 * N * L * L * C)
+            for e in engines:
+                report(f"{e} spatial attention L={L} heads={heads}",
+                       timeit(lambda: ops.attention_d64(qkv, N, L, heads, out, engine=e), once=args.once), 4.0 * N * L * L * C)
             report(f"temporal attention S={L} heads={heads}",
                    timeit(lambda: ops.temporal_attention_d64(qkv, 2, T, L, heads, out), once=args.once), 4.0 * N * L * T * C,
                    8.0 * M * C)
