@@ -25,8 +25,8 @@ int validate_gemm(const hi3d_gemm_params* p, const char* who);
 
 constexpr int T5_BM = 128;
 constexpr int T5_BK = 64;
-constexpr int T5_THREADS = 320;
-constexpr int T5_EPI_WARPS = 8;
+constexpr int T5_EPI_WARPS = 16;
+constexpr int T5_THREADS = 64 + 32 * T5_EPI_WARPS;
 constexpr int T5_MAX_MAPS = 4;
 constexpr int T5_MAX_STAGES = 8;
 constexpr int T5_A_BYTES = T5_BM * 128;
@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       }
     }
   } else {
-    // ======================= epilogue warps (2..9) =======================
+    // ======================= epilogue warps (2..17): 4 per TMEM lane quarter =======================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int half_sel = (warp - 2) >> 2;        // which of the alternating 32-column chunks
+    const int wsel = (warp - 2) >> 2;            // this warp takes 32-column chunks wsel, wsel + EPI/4, ...
     const bool geglu = (p.act == HI3D_ACT_GEGLU);
     const int rl = q * 32 + lane;                // tile-local row == TMEM lane
     uint32_t at = 0;
@@ -231,25 +231,39 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       {
         const int et = tid - 64;
         const int nb = n0 + et;
-        sbias[buf * 256 + et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (et < 256) sbias[buf * 256 + et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T5_EPI_WARPS) : "memory");
       }
       const float* sb = sbias + buf * 256;
       mbar_wait(bar_acc_full + 8 * buf, (at >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = half_sel * 32; c0 < BN; c0 += 64) {
+      for (int c0 = wsel * 32; c0 < BN; c0 += 8 * T5_EPI_WARPS) {
         uint32_t v[32];
         tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
         const int n = n0 + c0;
         const bool live = (m >= 0) && (n < p.N);
-        // issue the row-bias loads while the TMEM read is in flight
-        Half8 rb8[4];
-        if (rbp != nullptr && live) {
+        // issue every global load of this chunk while the TMEM read is in flight
+        Half8 rb8[4], rs8[4], bx8[4];
+        if (live) {
+          if (rbp != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (n + 8 * j < p.N) rb8[j] = *reinterpret_cast<const Half8*>(rbp + n + 8 * j);
+            for (int j = 0; j < 4; j++)
+              if (n + 8 * j < p.N) rb8[j] = *reinterpret_cast<const Half8*>(rbp + n + 8 * j);
+          }
+          if (p.residual != nullptr) {
+            const __half* rp = p.residual + m * p.res_ld + n;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (n + 8 * j < p.N) rs8[j] = *reinterpret_cast<const Half8*>(rp + 8 * j);
+          }
+          if (p.blend_x != nullptr) {
+            const __half* xp = p.blend_x + m * p.blend_ld + n;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (n + 8 * j < p.N) bx8[j] = *reinterpret_cast<const Half8*>(xp + 8 * j);
+          }
         }
         tmem_ld_wait(v);
         if (!live) continue;
@@ -289,11 +303,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 2) o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(f[j], f[j + 1]);
           if (p.residual != nullptr) {
-            const __half* rp = p.residual + m * p.res_ld + n;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
               if (n + 8 * c >= p.N) break;
-              const Half8 r8 = *reinterpret_cast<const Half8*>(rp + 8 * c);
+              const Half8 r8 = rs8[c];
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const float2 a = __half22float2(o8[c].h[k]), b = __half22float2(r8.h[k]);
@@ -302,12 +315,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
             }
           }
           if (p.blend_x != nullptr) {
-            const __half* xp = p.blend_x + m * p.blend_ld + n;
             const float al = p.alpha, be = 1.f - p.alpha;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
               if (n + 8 * c >= p.N) break;
-              const Half8 x8 = *reinterpret_cast<const Half8*>(xp + 8 * c);
+              const Half8 x8 = bx8[c];
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const float2 a = __half22float2(o8[c].h[k]), b = __half22float2(x8.h[k]);
