@@ -6,7 +6,9 @@
 //                    P written back as packed fp16 into the first 64 columns of the same S[b] region
 //   O_j = P V        tcgen05.mma, A = P (TMEM), B = V tile (smem, MN-major: rows = keys)    -> TMEM O[b]   (64 fp32 cols)
 //   O   = O * corr_j + O_j   in the row-owner's registers (fp32), so the accumulator never needs an in-TMEM rescale
-// S and O are double buffered: Q K^T of tile j+1 is issued before the softmax of tile j has finished.
+// 256 TMEM columns per CTA (S/P: 128, two O buffers: 2 x 64) and ~114 KB of shared memory, so TWO CTAs share an SM:
+// while one CTA's softmax warps work on a tile the other CTA's MMAs run, which keeps both the MUFU/FMA pipes and the
+// tensor pipe busy without splitting the softmax state across warpgroups.
 // Warp roles (192 threads): warp 0 = TMA producer (Q once, K/V ring), warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = softmax / accumulate / store.
 #include <cuda.h>
@@ -19,7 +21,7 @@ namespace hi3d {
 
 constexpr int FA_BM = 128;           // queries per CTA
 constexpr int FA_BN = 128;           // keys per tile
-constexpr int FA_STAGES = 3;         // K/V ring depth
+constexpr int FA_STAGES = 2;         // K/V ring depth per CTA (two CTAs per SM -> 4 tiles in flight per SM)
 constexpr int FA_THREADS = 192;
 constexpr int FA_TILE_BYTES = 128 * 128;                 // 128 rows x 64 fp16
 constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256 + 1024;
@@ -37,7 +39,7 @@ struct FaParams {
   __half* out;
 };
 
-__global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_constant__ FaParams p) {
+__global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -48,8 +50,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_co
   const uint32_t bar_q = bar0;                                // Q landed
   const uint32_t bar_kv_full = bar0 + 8;                      // [STAGES]
   const uint32_t bar_kv_empty = bar_kv_full + 8 * FA_STAGES;  // [STAGES]
-  const uint32_t bar_s_full = bar_kv_empty + 8 * FA_STAGES;   // [2]  S[b] written by the MMA
-  const uint32_t bar_p_full = bar_s_full + 16;                // [2]  P[b] written by the softmax warps
+  const uint32_t bar_s_full = bar_kv_empty + 8 * FA_STAGES;   // S written by the MMA (phase flips every tile)
+  const uint32_t bar_p_full = bar_s_full + 16;                // P written by the softmax warps
   const uint32_t bar_o_full = bar_p_full + 16;                // [2]  O[b] written by the MMA
   const uint32_t bar_o_empty = bar_o_full + 16;               // [2]  O[b] consumed by the softmax warps
   const uint32_t tmem_slot = bar_o_empty + 16;
@@ -64,24 +66,24 @@ __global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     mbar_init(bar_q, 1);
     for (int s = 0; s < FA_STAGES; s++) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_p_full, 4);
     for (int b = 0; b < 2; b++) {
-      mbar_init(bar_s_full + 8 * b, 1);
-      mbar_init(bar_p_full + 8 * b, 4);
       mbar_init(bar_o_full + 8 * b, 1);
       mbar_init(bar_o_empty + 8 * b, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
-  // TMEM columns: S[0] = [0,128), S[1] = [128,256), O[0] = [256,320), O[1] = [320,384)
-  const uint32_t tS0 = tmem_base, tO0 = tmem_base + 256;
+  // TMEM columns: S / P = [0,128), O[0] = [128,192), O[1] = [192,256)
+  const uint32_t tS0 = tmem_base, tO0 = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -103,28 +105,23 @@ __global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_co
       const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
       const uint64_t qd = umma_desc_sw128(sQ);
       mbar_wait(bar_q, 0);
-      auto issue_qk = [&](int j) {
-        const int s = j % FA_STAGES;
+      for (int j = 0; j < nkv; j++) {
+        const int b = j & 1, s = j % FA_STAGES;
         mbar_wait(bar_kv_full + 8 * s, (j / FA_STAGES) & 1);
         tc_fence_after();
+        // S = Q K^T.  The S/P columns are free: P V of tile j-1 was issued before and tcgen05.mma executes in order.
         const uint64_t kd = umma_desc_sw128(sKV + s * 2 * FA_TILE_BYTES);
-        const uint32_t tS = tS0 + (j & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < 4; k++) tc_mma_f16(tS, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
-        tc_commit(bar_s_full + 8 * (j & 1));
-      };
-      issue_qk(0);
-      for (int j = 0; j < nkv; j++) {
-        if (j + 1 < nkv) issue_qk(j + 1);           // overlaps the softmax of tile j
-        const int b = j & 1, s = j % FA_STAGES;
-        mbar_wait(bar_p_full + 8 * b, (j >> 1) & 1);           // P[b] of tile j is in TMEM
+        for (int k = 0; k < 4; k++) tc_mma_f16(tS0, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
+        tc_commit(bar_s_full);
+        mbar_wait(bar_p_full, j & 1);                           // P of tile j is in TMEM
         mbar_wait(bar_o_empty + 8 * b, ((j >> 1) & 1) ^ 1);    // O[b] of tile j-2 has been consumed
         tc_fence_after();
         const uint64_t vd = umma_desc_sw128_mn(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES);
-        const uint32_t tP = tS0 + b * 128, tO = tO0 + b * 64;
+        const uint32_t tO = tO0 + b * 64;
 #pragma unroll
         for (int k = 0; k < 8; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
-          tc_mma_f16_ts(tO, tP + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, k ? 1u : 0u);
+          tc_mma_f16_ts(tO, tS0 + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, k ? 1u : 0u);
         tc_commit(bar_o_full + 8 * b);
         tc_commit(bar_kv_empty + 8 * s);
       }
@@ -140,10 +137,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_co
     for (int i = 0; i < 64; i++) oacc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
     for (int j = 0; j < nkv; j++) {
-      const int b = j & 1;
-      mbar_wait(bar_s_full + 8 * b, (j >> 1) & 1);
+      mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
-      const uint32_t tS = tS0 + b * 128 + lane_off;
+      const uint32_t tS = tS0 + lane_off;
       // pass 1: row max
       float mx = m_run;
 #pragma unroll 1
@@ -178,7 +174,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_co
       l_run = l_run * corr + rs;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p_full + 8 * b);
+      if (lane == 0) mbar_arrive(bar_p_full);
       // fold in the previous tile's P V while the tensor core works on this one
       if (j > 0) {
         const int pb = (j - 1) & 1;
@@ -227,7 +223,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) fmha_tc5_kernel(const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256));
   }
 }
 
@@ -240,7 +236,7 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
     set_error("hi3d_attention_d64_tc5: bad arguments (n_img=%d L=%d heads=%d)", n_img, L, heads);
     return -2;
   }
-  if ((L % FA_BN) || heads > 65535 || n_img > 65535)      // ragged / tiny sequences: mma.sync kernel (same results)
+  if ((L % FA_BN) || L < 512 || heads > 65535 || n_img > 65535)   // ragged / short sequences: mma.sync kernel (same results)
     return hi3d_attention_d64(qkv, n_img, L, heads, scale, out, stream);
   FaParams fp;
   memset(&fp, 0, sizeof(fp));

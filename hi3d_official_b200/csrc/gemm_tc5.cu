@@ -15,6 +15,7 @@
 // warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating 32-column chunks).  Two accumulator
 // buffers (TMEM columns [0,256) and [256,512)) let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -45,6 +46,7 @@ struct T5Params {
   int nseg;
   int M, N, K, mode;
   int BN, stages, n_tiles, total_tiles;
+  int dbg;   // HI3D_TC5_DBG bit mask for bottleneck experiments: 1 skip stores, 2 skip residual/blend/rowbias loads, 4 skip TMEM loads, 8 skip MMA
   // tile -> rows
   int tw, th, tn;      // CONV2D patch (PLAIN: tw = 128, th = tn = 1; TEMPORAL: tw = ts, th = tf)
   int Wo, Ho, Nimg;    // CONV2D: output W, H, images.  TEMPORAL: Wo = HW, Ho = T, Nimg = B
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           const uint64_t ad = umma_desc_sw128(sA), bd = umma_desc_sw128(sA + T5_A_BYTES);
 #pragma unroll
           for (int k = 0; k < T5_BK / 16; k++)   // +32 bytes along K inside the 128-byte swizzle atom
-            tc_mma_f16(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
+            if (!(p.dbg & 8)) tc_mma_f16(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
           tc_commit(bar_empty + 8 * s);          // frees the smem slot when these MMAs retire
         }
         tc_commit(bar_acc_full + 8 * buf);       // accumulator complete
@@ -241,12 +243,13 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
 #pragma unroll 1
       for (int c0 = wsel * 32; c0 < BN; c0 += 8 * T5_EPI_WARPS) {
         uint32_t v[32];
-        tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
+        if (!(p.dbg & 4)) tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
         const int n = n0 + c0;
         const bool live = (m >= 0) && (n < p.N);
+        const bool ldok = live && !(p.dbg & 2);
         // issue every global load of this chunk while the TMEM read is in flight
         Half8 rb8[4], rs8[4], bx8[4];
-        if (live) {
+        if (ldok) {
           if (rbp != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -292,8 +295,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           for (int j = 0; j < 16; j += 2)
             o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(f[2 * j] * gelu_fast(f[2 * j + 1]), f[2 * j + 2] * gelu_fast(f[2 * j + 3]));
           __half* dst = p.out + m * p.out_ld + (n >> 1);
-          *reinterpret_cast<Half8*>(dst) = o8[0];
-          if (n + 16 < p.N) *reinterpret_cast<Half8*>(dst + 8) = o8[1];
+          if (!(p.dbg & 1)) {
+            *reinterpret_cast<Half8*>(dst) = o8[0];
+            if (n + 16 < p.N) *reinterpret_cast<Half8*>(dst + 8) = o8[1];
+          }
         } else {
           if (p.act == HI3D_ACT_SILU) {
 #pragma unroll
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           __half* dst = p.out + m * p.out_ld + n;
 #pragma unroll
           for (int c = 0; c < 4; c++)
-            if (n + 8 * c < p.N) *reinterpret_cast<Half8*>(dst + 8 * c) = o8[c];
+            if (n + 8 * c < p.N && !(p.dbg & 1)) *reinterpret_cast<Half8*>(dst + 8 * c) = o8[c];
         }
       }
       // this warp is done reading the accumulator buffer
@@ -492,6 +497,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.rb_ld = p->rb_ld; tp.act = p->act; tp.residual = (const __half*)p->residual; tp.res_ld = p->res_ld;
   tp.blend_x = (const __half*)p->blend_x; tp.blend_ld = p->blend_ld; tp.alpha = p->alpha;
   tp.out = (__half*)p->out; tp.out_ld = p->out_ld;
+  { const char* e = getenv("HI3D_TC5_DBG"); tp.dbg = e ? atoi(e) : 0; }
 
   static bool attr_done = false;
   const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + 1024;
