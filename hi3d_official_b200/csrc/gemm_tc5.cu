@@ -26,12 +26,13 @@ int validate_gemm(const hi3d_gemm_params* p, const char* who);
 
 constexpr int T5_BM = 128;
 constexpr int T5_BK = 64;
-constexpr int T5_EPI_WARPS = 16;
+constexpr int T5_EPI_WARPS = 8;
 constexpr int T5_THREADS = 64 + 32 * T5_EPI_WARPS;
 constexpr int T5_MAX_MAPS = 4;
 constexpr int T5_MAX_STAGES = 8;
 constexpr int T5_A_BYTES = T5_BM * 128;
-constexpr int T5_SMEM_BUDGET = 200 * 1024;
+constexpr int T5_SMEM_BUDGET = 192 * 1024;
+constexpr int T5_SCR_BYTES = 32 * 80;                  // per-epilogue-warp transpose scratch
 
 struct T5Seg {
   int map;       // index into amap[]
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 32);
   float* sbias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64);   // [2][256]
+  uint8_t* scratch = smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048;                  // [EPI_WARPS][32 x 80]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KT = p.K / T5_BK;
@@ -215,21 +217,31 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       }
     }
   } else {
-    // ======================= epilogue warps (2..17): 4 per TMEM lane quarter =======================
+    // ======================= epilogue warps: T5_EPI_WARPS/4 per TMEM lane quarter =======================
+    // A thread owns one accumulator row (its TMEM lane).  Global traffic is NOT issued row-per-thread (16-byte pieces
+    // of 32 different rows per instruction are partial-sector writes and were 4x slower than the MMA main loop):
+    // every 32 x 32 chunk goes through a per-warp shared-memory transpose so that 4 lanes cover 64 contiguous bytes of
+    // one row (full 32-byte sectors) for the output stores and for the residual / blend loads alike.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int wsel = (warp - 2) >> 2;            // this warp takes 32-column chunks wsel, wsel + EPI/4, ...
+    const int ew = warp - 2;                     // epilogue warp index
+    const int wsel = ew >> 2;                    // this warp takes 32-column chunks wsel, wsel + EPI/4, ...
     const bool geglu = (p.act == HI3D_ACT_GEGLU);
     const int rl = q * 32 + lane;                // tile-local row == TMEM lane
+    uint8_t* scr = scratch + ew * T5_SCR_BYTES;  // 32 rows x 80 bytes (64 data + 16 pad)
+    const int crow = lane >> 2, cchk = lane & 3; // coalesced pattern: rows crow + 8 i, 16-byte chunk cchk
     uint32_t at = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, at++) {
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const T5Tile o = t5_origin(p, mt);
       const int n0 = nt * BN;
       const long long m = t5_row(p, mt, o, rl);
+      long long mrow[4];                         // global rows of the rows this lane touches in the coalesced pattern
+#pragma unroll
+      for (int i = 0; i < 4; i++) mrow[i] = __shfl_sync(0xffffffffu, m, crow + 8 * i);
       const __half* rbp = nullptr;
       if (p.rowbias != nullptr && m >= 0) rbp = p.rowbias + (long long)((m / p.rb_div) % p.rb_mod) * p.rb_ld;
       const uint32_t buf = at & 1;
-      // stage this tile's bias slice in shared memory (one float per epilogue thread), then sync the epilogue warps
+      // stage this tile's bias slice in shared memory, then sync the epilogue warps
       {
         const int et = tid - 64;
         const int nb = n0 + et;
@@ -246,30 +258,27 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
         if (!(p.dbg & 4)) tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
         const int n = n0 + c0;
         const bool live = (m >= 0) && (n < p.N);
-        const bool ldok = live && !(p.dbg & 2);
-        // issue every global load of this chunk while the TMEM read is in flight
-        Half8 rb8[4], rs8[4], bx8[4];
-        if (ldok) {
-          if (rbp != nullptr) {
+        const bool colok = (n + cchk * 8) < p.N;                   // this lane's 16-byte column group exists
+        // issue every global load of this chunk (coalesced pattern) while the TMEM read is in flight
+        Half8 rb8[4], rsg[4], bxg[4];
+        if (!(p.dbg & 2)) {
+          if (rbp != nullptr && live) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
               if (n + 8 * j < p.N) rb8[j] = *reinterpret_cast<const Half8*>(rbp + n + 8 * j);
           }
           if (p.residual != nullptr) {
-            const __half* rp = p.residual + m * p.res_ld + n;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (n + 8 * j < p.N) rs8[j] = *reinterpret_cast<const Half8*>(rp + 8 * j);
+            for (int i = 0; i < 4; i++)
+              if (mrow[i] >= 0 && colok) rsg[i] = *reinterpret_cast<const Half8*>(p.residual + mrow[i] * p.res_ld + n + cchk * 8);
           }
           if (p.blend_x != nullptr) {
-            const __half* xp = p.blend_x + m * p.blend_ld + n;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (n + 8 * j < p.N) bx8[j] = *reinterpret_cast<const Half8*>(xp + 8 * j);
+            for (int i = 0; i < 4; i++)
+              if (mrow[i] >= 0 && colok) bxg[i] = *reinterpret_cast<const Half8*>(p.blend_x + mrow[i] * p.blend_ld + n + cchk * 8);
           }
         }
         tmem_ld_wait(v);
-        if (!live) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
           f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
-        if (rbp != nullptr) {
+        if (rbp != nullptr && live) {
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             if (n + 8 * j >= p.N) break;
@@ -289,53 +298,60 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           }
         }
         if (geglu) {
-          // 32 accumulator columns = 16 (value, gate) pairs -> 16 outputs = 32 bytes
+          // 32 accumulator columns = 16 (value, gate) pairs -> 16 outputs = 32 bytes per row
           Half8 o8[2];
 #pragma unroll
           for (int j = 0; j < 16; j += 2)
             o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(f[2 * j] * gelu_fast(f[2 * j + 1]), f[2 * j + 2] * gelu_fast(f[2 * j + 3]));
-          __half* dst = p.out + m * p.out_ld + (n >> 1);
-          if (!(p.dbg & 1)) {
-            *reinterpret_cast<Half8*>(dst) = o8[0];
-            if (n + 16 < p.N) *reinterpret_cast<Half8*>(dst + 8) = o8[1];
+          *reinterpret_cast<Half8*>(scr + lane * 80) = o8[0];
+          *reinterpret_cast<Half8*>(scr + lane * 80 + 16) = o8[1];
+          __syncwarp();
+          // 2 lanes per row: rows (lane >> 1) + 16 i
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int rr = (lane >> 1) + 16 * i, ck = lane & 1;
+            const long long mr = __shfl_sync(0xffffffffu, m, rr);
+            const Half8 w8 = *reinterpret_cast<const Half8*>(scr + rr * 80 + ck * 16);
+            if (mr >= 0 && n + 16 * ck < p.N && !(p.dbg & 1))
+              *reinterpret_cast<Half8*>(p.out + mr * p.out_ld + (n >> 1) + 8 * ck) = w8;
           }
+          __syncwarp();
         } else {
           if (p.act == HI3D_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; j++) f[j] = silu_f(f[j]);
           }
-          Half8 o8[4];
+          // row-per-thread values -> shared -> coalesced pattern
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(f[j], f[j + 1]);
-          if (p.residual != nullptr) {
+          for (int c = 0; c < 4; c++) {
+            Half8 o8;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-              if (n + 8 * c >= p.N) break;
-              const Half8 r8 = rs8[c];
+            for (int k = 0; k < 4; k++) o8.h[k] = __floats2half2_rn(f[8 * c + 2 * k], f[8 * c + 2 * k + 1]);
+            *reinterpret_cast<Half8*>(scr + lane * 80 + 16 * c) = o8;
+          }
+          __syncwarp();
+          const float al = p.alpha, be = 1.f - p.alpha;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            Half8 w8 = *reinterpret_cast<const Half8*>(scr + (crow + 8 * i) * 80 + cchk * 16);
+            if (mrow[i] < 0 || !colok) continue;
+            if (p.residual != nullptr && !(p.dbg & 2)) {
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                const float2 a = __half22float2(o8[c].h[k]), b = __half22float2(r8.h[k]);
-                o8[c].h[k] = __floats2half2_rn(a.x + b.x, a.y + b.y);
+                const float2 a = __half22float2(w8.h[k]), b = __half22float2(rsg[i].h[k]);
+                w8.h[k] = __floats2half2_rn(a.x + b.x, a.y + b.y);
               }
             }
-          }
-          if (p.blend_x != nullptr) {
-            const float al = p.alpha, be = 1.f - p.alpha;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-              if (n + 8 * c >= p.N) break;
-              const Half8 x8 = bx8[c];
+            if (p.blend_x != nullptr && !(p.dbg & 2)) {
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                const float2 a = __half22float2(o8[c].h[k]), b = __half22float2(x8.h[k]);
-                o8[c].h[k] = __floats2half2_rn(al * b.x + be * a.x, al * b.y + be * a.y);
+                const float2 a = __half22float2(w8.h[k]), b = __half22float2(bxg[i].h[k]);
+                w8.h[k] = __floats2half2_rn(al * b.x + be * a.x, al * b.y + be * a.y);
               }
             }
+            if (!(p.dbg & 1)) *reinterpret_cast<Half8*>(p.out + mrow[i] * p.out_ld + n + cchk * 8) = w8;
           }
-          __half* dst = p.out + m * p.out_ld + n;
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            if (n + 8 * c < p.N && !(p.dbg & 1)) *reinterpret_cast<Half8*>(dst + 8 * c) = o8[c];
+          __syncwarp();
         }
       }
       // this warp is done reading the accumulator buffer
@@ -500,7 +516,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   { const char* e = getenv("HI3D_TC5_DBG"); tp.dbg = e ? atoi(e) : 0; }
 
   static bool attr_done = false;
-  const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + 1024;
+  const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
     if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
@@ -511,7 +527,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     attr_done = true;
   }
   const int grid = tp.total_tiles < g_sm_count ? tp.total_tiles : g_sm_count;
-  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + 1024;
+  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
   gemm_tc5_kernel<<<grid, T5_THREADS, smem, st>>>(tp);
   return check_launch("hi3d_gemm_tc5");
 }
