@@ -463,16 +463,25 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   }
   if (!ok) return hi3d_gemm(p, stream);
 
-  // tile-N: multiple of 32 in [32, 256] with the least padded work; ties go to the wider tile
+  // tile-N: multiple of 32 in [32, 256].  Cost model = rounds of the persistent grid x time per tile, where a tile
+  // costs its MMA columns plus a fixed term (A-operand traffic / epilogue set-up); this accounts both for the padding
+  // of N and for wave quantisation over the SMs (e.g. N = 1280 with 64 row-tiles: 5 x 256 -> 3 rounds, 8 x 160 -> 4
+  // rounds of much shorter tiles).  Ties go to the wider tile.
+  if (g_sm_count <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
   int BN = 256;
   {
     long long best = -1;
     for (int cand = 256; cand >= 32; cand -= 32) {
       if (p->act == HI3D_ACT_GEGLU && (cand % 64)) continue;     // keep GEGLU output chunks 32-byte aligned
-      const long long cost = (long long)((p->N + cand - 1) / cand) * cand;
-      // prefer >= 128 unless a narrower tile removes more than ~12% padding
-      const long long adj = cand >= 128 ? cost * 8 : cost * 9;
-      if (best < 0 || adj < best) { best = adj; BN = cand; }
+      const long long ntl = (p->N + cand - 1) / cand;
+      const long long rounds = ((long long)m_tiles * ntl + g_sm_count - 1) / g_sm_count;
+      const long long cost = rounds * (cand + 48);
+      if (best < 0 || cost < best) { best = cost; BN = cand; }
     }
   }
   const int stage_bytes = T5_A_BYTES + BN * 128;
