@@ -255,6 +255,7 @@ def main():
     from hi3d_official_b200 import _native, configs, spec
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     model = configs.build_engine(args.stage, device=dev)

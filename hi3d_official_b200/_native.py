@@ -110,5 +110,14 @@ def check(rc: int, what: str = ""):
         raise Hi3dError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
 
 
+_replayed = 0      # launches executed through CUDA-graph replays (the C counter only sees eager / capture-time calls)
+
+
 def launch_count() -> int:
-    return int(load().hi3d_launch_count())
+    return int(load().hi3d_launch_count()) + _replayed
+
+
+def note_graph_replay(n_launches: int):
+    """A CUDA graph holding `n_launches` of this library's kernels was replayed once."""
+    global _replayed
+    _replayed += int(n_launches)

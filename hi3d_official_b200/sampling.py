@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _native, ops
 from .unet import CIN_PAD, VideoUNet
 from .util import append_dims, append_zero, default, instantiate_from_config
 
@@ -262,10 +262,14 @@ class _FusedState:
                 self._launch(self._gx, self._gs, self._gsn, self._gxo, None)        # eager warm-up (lazy one-time init)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                n0 = _native.launch_count()
                 with torch.cuda.graph(g):
                     self._launch(self._gx, self._gs, self._gsn, self._gxo, None)
+                self._graph_launches = _native.launch_count() - n0
+                _native.note_graph_replay(-self._graph_launches)      # capture-time calls did not execute
                 self._graph = g
             self._graph.replay()
+            _native.note_graph_replay(self._graph_launches)
             return self._gxo.clone()
         plan = self.plan
         x = x.contiguous()
