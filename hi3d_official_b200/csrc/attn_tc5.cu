@@ -141,36 +141,50 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
       tc_fence_after();
       const uint32_t tS = tS0 + lane_off;
       // pass 1: row max
-      float mx = m_run;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; cc++) {
-        uint32_t v[32];
-        tmem_ld32(tS + 32 * cc, v);
-        tmem_ld_wait(v);
+      // (two 32-column TMEM reads in flight, 8 independent max chains: the reduction is latency-, not issue-bound)
+      float mxa[8];
 #pragma unroll
-        for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(v[i]));
+      for (int i = 0; i < 8; i++) mxa[i] = m_run;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tS + 32 * cc, v0);
+        tmem_ld32(tS + 32 * cc + 32, v1);
+        tmem_ld_wait(v0);
+#pragma unroll
+        for (int i = 0; i < 32; i++) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v0[i]));
+        tmem_ld_wait(v1);
+#pragma unroll
+        for (int i = 0; i < 32; i++) mxa[4 + (i & 3)] = fmaxf(mxa[4 + (i & 3)], __uint_as_float(v1[i]));
       }
+      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
       const float corr = exp2f((m_run - mx) * c);       // m_run = -inf on the first tile -> 0
       const float moff = mx * c;
       m_run = mx;
-      // pass 2: P = exp2(S*c - m*c), row sum, packed fp16 back into the same TMEM region
-      float rs = 0.f;
-#pragma unroll 1
+      // pass 2: P = exp2(S*c - m*c), row sum (4 independent chains), packed fp16 back into the same TMEM region;
+      // the TMEM read of chunk cc+1 is issued before chunk cc is processed
+      float rsa[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t va[32], vb[32];
+      tmem_ld32(tS, va);
+#pragma unroll
       for (int cc = 0; cc < 4; cc++) {
-        uint32_t v[32];
-        tmem_ld32(tS + 32 * cc, v);
-        tmem_ld_wait(v);
+        uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+        uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+        tmem_ld_wait(cur);
+        if (cc + 1 < 4) tmem_ld32(tS + 32 * (cc + 1), nxt);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx_ftz(fmaf(__uint_as_float(v[i]), c, -moff));
-          const float p1 = ex2_approx_ftz(fmaf(__uint_as_float(v[i + 1]), c, -moff));
-          rs += p0 + p1;
+          const float p0 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i]), c, -moff));
+          const float p1 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i + 1]), c, -moff));
+          rsa[(i >> 1) & 3] += p0 + p1;
           pk[i >> 1] = pack_half2(p0, p1);
         }
         tmem_st16(tS + 16 * cc, pk);
       }
       tmem_st_wait();
+      const float rs = (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
       l_run = l_run * corr + rs;
       tc_fence_before();
       __syncwarp();

@@ -26,7 +26,7 @@ int validate_gemm(const hi3d_gemm_params* p, const char* who);
 
 constexpr int T5_BM = 128;
 constexpr int T5_BK = 64;
-constexpr int T5_EPI_WARPS = 12;
+constexpr int T5_EPI_WARPS = 8;
 constexpr int T5_THREADS = 64 + 32 * T5_EPI_WARPS;
 constexpr int T5_MAX_MAPS = 4;
 constexpr int T5_MAX_STAGES = 8;
