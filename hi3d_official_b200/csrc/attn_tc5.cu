@@ -259,7 +259,7 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
     cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)n_img * (cuuint64_t)L};
     cuuint64_t str[1] = {(cuuint64_t)(3 * C) * 2};
     cuuint32_t box[2] = {64, 128};
-    if (encode_map(&fp.qkv_map, qkv, 2, dims, str, box)) return -1;
+    if (encode_map(&fp.qkv_map, qkv, 2, dims, str, box, nullptr)) return -1;
   }
   fp.L = L; fp.C = C; fp.heads = heads;
   fp.scale_log2 = scale * 1.4426950408889634f;

@@ -241,9 +241,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mma_kernel(const __grid_
     const int m = m0 + r;
     const int nc = nout0 + c * 8;
     if (m >= p.M || nc >= Nout) continue;
+    long long mo = m;                       // output row (differs from m only for the parity-class upsample convs)
+    if (p.out_up) {
+      const int n_ = m / HW, rem_ = m - n_ * HW;
+      const int y_ = rem_ / p.Wo, x_ = rem_ - y_ * p.Wo;
+      mo = ((long long)n_ * 2 * p.Ho + 2 * y_ + p.out_py) * (2 * p.Wo) + 2 * x_ + p.out_px;
+    }
     Half8 v = *reinterpret_cast<const Half8*>(sC + r * pitch + c * 8);
     if (res != nullptr) {
-      Half8 rr = *reinterpret_cast<const Half8*>(res + (long long)m * p.res_ld + nc);
+      Half8 rr = *reinterpret_cast<const Half8*>(res + mo * p.res_ld + nc);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         float2 a = __half22float2(v.h[q]), b = __half22float2(rr.h[q]);
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mma_kernel(const __grid_
       }
     }
     if (bx != nullptr) {
-      Half8 xx = *reinterpret_cast<const Half8*>(bx + (long long)m * p.blend_ld + nc);
+      Half8 xx = *reinterpret_cast<const Half8*>(bx + mo * p.blend_ld + nc);
       const float al = p.alpha, be = 1.f - p.alpha;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mma_kernel(const __grid_
         v.h[q] = __floats2half2_rn(al * b.x + be * a.x, al * b.y + be * a.y);
       }
     }
-    *reinterpret_cast<Half8*>(out + (long long)m * p.out_ld + nc) = v;
+    *reinterpret_cast<Half8*>(out + mo * p.out_ld + nc) = v;
   }
 }
 
@@ -312,6 +318,13 @@ int validate_gemm(const hi3d_gemm_params* p, const char* who) {
                 p->Ws, p->stride, p->ups, p->M);
       return -2;
     }
+    if (p->out_up && (p->stride != 1 || p->ups != 0 || (p->out_py & ~1) || (p->out_px & ~1))) {
+      set_error("%s: out_up needs stride 1, ups 0 and parities in {0,1}", who);
+      return -2;
+    }
+  } else if (p->out_up) {
+    set_error("%s: out_up is a CONV2D option", who);
+    return -2;
   } else if (p->mode == HI3D_ROWS_TEMPORAL) {
     if (p->T <= 0 || p->Ho * p->Wo <= 0 || (p->M % (p->T * p->Ho * p->Wo))) {
       set_error("%s: bad temporal geometry T=%d HW=%d M=%d", who, p->T, p->Ho * p->Wo, p->M);

@@ -52,6 +52,8 @@ struct T5Params {
   int tw, th, tn;      // CONV2D patch (PLAIN: tw = 128, th = tn = 1; TEMPORAL: tw = ts, th = tf)
   int Wo, Ho, Nimg;    // CONV2D: output W, H, images.  TEMPORAL: Wo = HW, Ho = T, Nimg = B
   int tiles_x, tiles_y;  // tiles along W and H (CONV2D) / along HW and T (TEMPORAL)
+  int cstride;           // CONV2D input stride (1 | 2): TMA element strides, box origin = tile origin * cstride + tap
+  int out_up, out_py, out_px;   // parity-class output mapping (see hi3d_gemm_params::out_up)
   // epilogue
   const float* bias;
   const __half* rowbias;
@@ -118,6 +120,15 @@ HI3D_DEVINL long long t5_row(const T5Params& p, int mt, const T5Tile& o, int r) 
   return ((long long)n * p.Ho + y) * p.Wo + x;
 }
 
+// base row (row of the Ho x Wo GEMM grid) -> row of the output tensor
+HI3D_DEVINL long long t5_map(const T5Params& p, long long m) {
+  if (!p.out_up || m < 0) return m;
+  const int hw = p.Ho * p.Wo;
+  const int n = (int)(m / hw), rem = (int)(m - (long long)n * hw);
+  const int y = rem / p.Wo, x = rem - y * p.Wo;
+  return ((long long)n * 2 * p.Ho + 2 * y + p.out_py) * (2 * p.Wo) + 2 * x + p.out_px;
+}
+
 __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ T5Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           if (p.mode == HI3D_ROWS_PLAIN)
             tma_load_2d(sA, &p.amap[sg.map], full, c, mt * T5_BM);
           else if (p.mode == HI3D_ROWS_CONV2D)
-            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0 + sg.dx, o.y0 + sg.dy, o.z0);
+            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
           else
             tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0, o.y0 + sg.dt, o.z0);
           tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       const long long m = t5_row(p, mt, o, rl);
       long long mrow[4];                         // global rows of the rows this lane touches in the coalesced pattern
 #pragma unroll
-      for (int i = 0; i < 4; i++) mrow[i] = __shfl_sync(0xffffffffu, m, crow + 8 * i);
+      for (int i = 0; i < 4; i++) mrow[i] = t5_map(p, __shfl_sync(0xffffffffu, m, crow + 8 * i));
       const __half* rbp = nullptr;
       if (p.rowbias != nullptr && m >= 0) rbp = p.rowbias + (long long)((m / p.rb_div) % p.rb_mod) * p.rb_ld;
       const uint32_t buf = at & 1;
@@ -385,10 +396,11 @@ static EncodeTiledFn get_encode() {
 }
 
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+               const cuuint32_t* box, const cuuint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("hi3d_gemm_tc5: cuTensorMapEncodeTiled entry point unavailable"); return -1; }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides) for (int i = 0; i < rank; i++) estr[i] = elem_strides[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -416,6 +428,8 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   T5Params tp;
   memset(&tp, 0, sizeof(tp));
   tp.M = p->M; tp.N = p->N; tp.K = p->K; tp.mode = p->mode; tp.nseg = p->nseg;
+  tp.cstride = (p->mode == HI3D_ROWS_CONV2D) ? p->stride : 1;
+  tp.out_up = p->out_up; tp.out_py = p->out_py; tp.out_px = p->out_px;
   int m_tiles = 0;
   bool ok = (p->N >= 32) && (p->N % 8 == 0);
   // the vectorised epilogue needs 16-byte aligned rows / bias
@@ -424,7 +438,8 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     tp.tw = 128; tp.th = 1; tp.tn = 1;
     m_tiles = (p->M + T5_BM - 1) / T5_BM;
   } else if (p->mode == HI3D_ROWS_CONV2D) {
-    ok = ok && p->stride == 1 && p->ups == 0 && p->Ho == p->Hs && p->Wo == p->Ws;
+    ok = ok && p->ups == 0 && ((p->stride == 1 && p->Ho == p->Hs && p->Wo == p->Ws) ||
+                               (p->stride == 2 && p->Hs == 2 * p->Ho && p->Ws == 2 * p->Wo && !p->out_up));
     const int Nimg = ok ? p->M / (p->Ho * p->Wo) : 0;
     int tw = 1;
     while (tw * 2 <= 16 && (p->Wo % (tw * 2)) == 0) tw *= 2;
@@ -498,25 +513,27 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
       cuuint64_t dims[2] = {ld, (cuuint64_t)p->M};
       cuuint64_t str[1] = {ld * 2};
       cuuint32_t box[2] = {64, 128};
-      if (encode_map(&tp.amap[j], srcs[j], 2, dims, str, box)) return -1;
+      if (encode_map(&tp.amap[j], srcs[j], 2, dims, str, box, nullptr)) return -1;
     } else if (p->mode == HI3D_ROWS_CONV2D) {
       cuuint64_t dims[4] = {ld, (cuuint64_t)p->Ws, (cuuint64_t)p->Hs, (cuuint64_t)tp.Nimg};
       cuuint64_t str[3] = {ld * 2, ld * 2 * p->Ws, ld * 2 * p->Ws * p->Hs};
-      cuuint32_t box[4] = {64, (cuuint32_t)tp.tw, (cuuint32_t)tp.th, (cuuint32_t)tp.tn};
-      if (encode_map(&tp.amap[j], srcs[j], 4, dims, str, box)) return -1;
+      const cuuint32_t cs = (cuuint32_t)tp.cstride;   // stride 2: box spans 2*tw x 2*th input pixels, every 2nd loaded
+      cuuint32_t box[4] = {64, (cuuint32_t)tp.tw * cs, (cuuint32_t)tp.th * cs, (cuuint32_t)tp.tn};
+      cuuint32_t est[4] = {1, cs, cs, 1};
+      if (encode_map(&tp.amap[j], srcs[j], 4, dims, str, box, est)) return -1;
     } else {
       const cuuint64_t HW = (cuuint64_t)tp.Wo, T = (cuuint64_t)tp.Ho;
       cuuint64_t dims[4] = {ld, HW, T, (cuuint64_t)tp.Nimg};
       cuuint64_t str[3] = {ld * 2, ld * 2 * HW, ld * 2 * HW * T};
       cuuint32_t box[4] = {64, (cuuint32_t)tp.tw, (cuuint32_t)tp.th, 1};
-      if (encode_map(&tp.amap[j], srcs[j], 4, dims, str, box)) return -1;
+      if (encode_map(&tp.amap[j], srcs[j], 4, dims, str, box, nullptr)) return -1;
     }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)p->N};
     cuuint64_t str[1] = {(cuuint64_t)p->K * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
-    if (encode_map(&tp.bmap, p->W, 2, dims, str, box)) return -1;
+    if (encode_map(&tp.bmap, p->W, 2, dims, str, box, nullptr)) return -1;
   }
   tp.bias = p->bias; tp.rowbias = (const __half*)p->rowbias; tp.rb_div = p->rb_div; tp.rb_mod = p->rb_mod;
   tp.rb_ld = p->rb_ld; tp.act = p->act; tp.residual = (const __half*)p->residual; tp.res_ld = p->res_ld;

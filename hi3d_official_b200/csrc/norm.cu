@@ -86,8 +86,8 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
 }
 
 // ---- pass 1b: combine the chunk partials of one sample into (mean, rstd) per group -------------------------
-// grid (n_samples), 256 threads; result at fin[n][32][2].
-__global__ void __launch_bounds__(256)
+// grid (n_samples), 1024 threads; result at fin[n][32][2].
+__global__ void __launch_bounds__(1024)
 gn_finalize_kernel(const float* __restrict__ ws, int nchunks, long long rows_per_sample, int cpg, float eps,
                    float* __restrict__ fin) {
   __shared__ float stot[GN_GROUPS * 2];
@@ -95,9 +95,17 @@ gn_finalize_kernel(const float* __restrict__ ws, int nchunks, long long rows_per
   if (tid < GN_GROUPS * 2) stot[tid] = 0.f;
   __syncthreads();
   const float* w = ws + (long long)n * GN_MAX_CHUNKS * (GN_GROUPS * 2);
-  float acc = 0.f;                                   // thread owns value index tid % 64, chunks tid/64, +4, ...
-  for (int c = tid >> 6; c < nchunks; c += 4) acc += w[c * (GN_GROUPS * 2) + (tid & 63)];
-  atomicAdd(&stot[tid & 63], acc);
+  // thread owns value index tid % 64 and chunks tid/64, +16, ...; 4 independent loads in flight per thread
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int c = tid >> 6;
+  for (; c + 48 < nchunks; c += 64) {
+    a0 += w[c * (GN_GROUPS * 2) + (tid & 63)];
+    a1 += w[(c + 16) * (GN_GROUPS * 2) + (tid & 63)];
+    a2 += w[(c + 32) * (GN_GROUPS * 2) + (tid & 63)];
+    a3 += w[(c + 48) * (GN_GROUPS * 2) + (tid & 63)];
+  }
+  for (; c < nchunks; c += 16) a0 += w[c * (GN_GROUPS * 2) + (tid & 63)];
+  atomicAdd(&stot[tid & 63], (a0 + a1) + (a2 + a3));
   __syncthreads();
   if (tid < GN_GROUPS) {
     const double cnt = (double)rows_per_sample * (double)cpg;
@@ -338,7 +346,7 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
   int rc = check_launch("hi3d_groupnorm_silu(stats)");
   if (rc) return rc;
   float* fin = ws + (long long)n_samples * GN_MAX_CHUNKS * GN_GROUPS * 2;
-  gn_finalize_kernel<<<n_samples, 256, 0, st>>>(ws, (int)chunks, rows_per_sample, C / GN_GROUPS, eps, fin);
+  gn_finalize_kernel<<<n_samples, 1024, 0, st>>>(ws, (int)chunks, rows_per_sample, C / GN_GROUPS, eps, fin);
   rc = check_launch("hi3d_groupnorm_silu(finalize)");
   if (rc) return rc;
   // ---- apply: same sizing rule (each CTA also re-reduces `chunks` x 64 partials, a few KB)

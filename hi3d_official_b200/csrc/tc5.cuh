@@ -121,6 +121,6 @@ HI3D_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n
 
 // host: encode a tiled fp16 tensor map with SWIZZLE_128B (defined in gemm_tc5.cu)
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box);
+               const cuuint32_t* box, const cuuint32_t* elem_strides);
 
 }  // namespace hi3d

@@ -83,6 +83,7 @@ class Gemm:
         p.Ho, p.Wo = g.get("Ho", 1), g.get("Wo", 1)
         p.Hs, p.Ws = g.get("Hs", p.Ho), g.get("Ws", p.Wo)
         p.stride, p.ups, p.T = g.get("stride", 1), g.get("ups", 0), g.get("T", 1)
+        p.out_up, p.out_py, p.out_px = g.get("out_up", 0), g.get("out_py", 0), g.get("out_px", 0)
         p.nseg = len(segs)
         for i, s in enumerate(segs):
             p.seg[i].src, p.seg[i].ld, p.seg[i].c_off, p.seg[i].C = s.src.data_ptr(), s.ld, s.c_off, s.C
@@ -110,7 +111,7 @@ class Gemm:
             p.blend_ld = blend_x.shape[-1]
         p.blend_x, p.alpha = _ptr(blend_x), float(alpha)
         p.out, p.out_ld = out.data_ptr(), out.shape[-1]
-        if out.shape[-1] < n_out or out.numel() < M * out.shape[-1]:
+        if out.shape[-1] < n_out or out.numel() < M * out.shape[-1] * (4 if p.out_up else 1):
             raise ValueError(f"out too small: {tuple(out.shape)} for M={M} N_out={n_out}")
         self.p = p
         self._keep = (list(segs), W, out, bias, rowbias, residual, blend_x)   # keep storages alive

@@ -52,6 +52,33 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Te
     return wi.to(F16).contiguous(), bi.contiguous()
 
 
+# nearest-x2 upsample followed by a 3x3 conv (openaimodel.py:154-156, model.py:67-71) == four parity-specific 2x2 convs on
+# the SOURCE grid: output pixel (2y+py, 2x+px) with tap dy reads source row y + floor((py+dy)/2), so the three taps of
+# one axis collapse onto two source shifts and their weights can be summed up front (4/9 of the FLOPs, no upsampled tensor).
+UP_SHIFTS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}     # parity -> ((shift, kernel indices), ...)
+
+
+def pack_upconv_parity(w: torch.Tensor):
+    """(Co, Ci, 3, 3) -> {(py, px): (fp16 [Co, 4*Ci], [(sy, sx), ...])}: K ordered like ops.conv_taps over the listed
+    (dy, dx) source shifts."""
+    co, ci = w.shape[:2]
+    wf = w.float()
+    out = {}
+    for py in (0, 1):
+        for px in (0, 1):
+            mats, shifts = [], []
+            for sy, kys in UP_SHIFTS[py]:
+                for sx, kxs in UP_SHIFTS[px]:
+                    acc = torch.zeros(co, ci, dtype=torch.float32, device=w.device)
+                    for ky in kys:
+                        for kx in kxs:
+                            acc += wf[:, :, ky, kx]
+                    mats.append(acc)
+                    shifts.append((sy, sx))
+            out[(py, px)] = (torch.cat(mats, dim=1).to(F16).contiguous(), shifts)
+    return out
+
+
 def cat_k(*mats: torch.Tensor) -> torch.Tensor:
     """Concatenate packed matrices along K (e.g. [3x3 conv | 1x1 skip] fused into one GEMM)."""
     return torch.cat(mats, dim=1).contiguous()

@@ -156,7 +156,7 @@ class VideoUNet(nn.Module):
             elif L.kind == "down":
                 P[n] = (pack.pack_conv2d(sd[n + "op.weight"]), pb(n + "op.bias"))
             elif L.kind == "up":
-                P[n] = (pack.pack_conv2d(sd[n + "conv.weight"]), pb(n + "conv.bias"))
+                P[n] = (pack.pack_upconv_parity(sd[n + "conv.weight"]), pb(n + "conv.bias"))
             elif L.kind == "res":
                 for sub, tconv in (("", False), ("time_stack.", True)):
                     q = n + sub
@@ -373,7 +373,7 @@ class _Plan:
                     cur = (out, L.cout, h, w)
                 elif L.kind == "up":
                     out = next_out(N * 4 * h * w, L.cout)
-                    self._conv(bl, [cur[0]], P[L.name], out, 2 * h, 2 * w, h, w, ups=1)
+                    self._upconv(bl, cur[0], P[L.name], out, h, w)
                     h, w = 2 * h, 2 * w
                     cur = (out, L.cout, h, w)
         # out: GN32 -> SiLU -> conv3x3 (video_model.py:436-440,500-501)
@@ -401,6 +401,16 @@ class _Plan:
         M = self.N * ho * wo
         self._gemm(lst, lambda: ops.conv_taps([s.t for s in srcs]), Wt, out, M, mode=ops.ROWS_CONV2D,
                    geom=dict(Ho=ho, Wo=wo, Hs=hs_, Ws=ws_, stride=stride, ups=ups), bias=b, **kw)
+
+    def _upconv(self, lst, src: LazyBuf, wb, out: LazyBuf, h, w, n_img=None):
+        """Upsample (nearest x2) + conv3x3 (openaimodel.py:154-156) as four parity-class 2x2 convs on the source
+        grid with pre-summed taps (pack.pack_upconv_parity): no upsampled tensor, 4/9 of the FLOPs."""
+        parity, b = wb
+        n_img = self.N if n_img is None else n_img
+        M = n_img * h * w
+        for (py, px), (Wt, shifts) in parity.items():
+            self._gemm(lst, lambda shifts=shifts: [ops.SegSpec(src.t, dy=sy, dx=sx) for sy, sx in shifts], Wt, out, M,
+                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=b)
 
     def _emb_slice(self, q):
         off, n = self.P["emb_off"][q]

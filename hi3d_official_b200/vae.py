@@ -171,7 +171,11 @@ class _VAEPlan:
                 bi = bo
             if lvl != 0:          # Upsample: nearest x2 + conv3x3 (model.py:67-71), fused into the gather
                 out = self._nxt(n * 4 * h * w, bi)
-                self._conv(cur, f"decoder.up.{lvl}.upsample.conv", out, 2 * h, 2 * w, h, w, ups=1)
+                parity, ub = self.P[f"decoder.up.{lvl}.upsample.conv"]
+                for (py, px), (Wt, shifts) in parity.items():   # nearest-x2 + conv3x3 == 4 parity-class 2x2 convs
+                    self._gemm(lambda shifts=shifts, cur=cur: [ops.SegSpec(cur.t, dy=sy, dx=sx) for sy, sx in shifts], Wt,
+                               out, n * h * w, mode=ops.ROWS_CONV2D,
+                               geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=ub)
                 cur, h, w = out, 2 * h, 2 * w
         M = n * h * w
         g = A.want("gn", M, bi)
@@ -261,6 +265,8 @@ class AutoencoderKL(nn.Module):
                 P[base] = (pack.pack_conv2d(w, cin_pad=CIN_PAD), b.float().contiguous())
             elif base == "encoder.conv_out":                   # 2*z channels -> padded to 64 (feeds quant_conv)
                 P[base] = (pack.pack_conv2d(w, cout_pad=64), pack.pack_bias(b, w.shape[0], 64))
+            elif base.endswith("upsample.conv"):
+                P[base] = (pack.pack_upconv_parity(w), b.float().contiguous())
             elif base == "decoder.conv_out":
                 P[base] = (pack.pack_conv2d(w, cout_pad=COUT_PAD), pack.pack_bias(b, w.shape[0], COUT_PAD))
             elif base == "quant_conv":                         # 1x1: K padded to 64, N padded to 8

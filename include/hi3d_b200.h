@@ -69,6 +69,10 @@ typedef struct {
   int32_t stride;           /* CONV2D: 1 or 2                                                          */
   int32_t ups;              /* CONV2D: 1 -> taps address the x2 nearest-upsampled source               */
   int32_t T;                /* TEMPORAL: frames per clip                                               */
+  int32_t out_up;           /* CONV2D: 1 -> rows index an (n, y, x) grid of Ho x Wo but are WRITTEN to the x2 grid at
+                               (2y + out_py, 2x + out_px): one parity class of nearest-x2 + conv3x3, which is a 2x2
+                               conv on the source grid with pre-summed taps (4 launches, 4/9 of the FLOPs)       */
+  int32_t out_py, out_px;
   int32_t nseg;
   hi3d_seg seg[HI3D_MAX_SEGS];
   const void* W;            /* fp16 [N, K], K contiguous, K ordered as the segments                    */

@@ -116,3 +116,36 @@ def test_tc5_unsupported_geometry_forwards_to_mma_engine():
     ops.Gemm(ops.conv_taps([xh]), pack.pack_conv2d(w), out, n * ho * ho, mode=ops.ROWS_CONV2D,
              geom=dict(Ho=ho, Wo=ho, Hs=hs, Ws=hs, stride=2), engine=E)()
     close(out.view(n, ho, ho, co).permute(0, 3, 1, 2), ref, name="stride-2 via fallback")
+
+
+@pytest.mark.parametrize("engine", ["mma", "tc5"])
+@pytest.mark.parametrize("n,ci,co,hs", [(2, 64, 128, 16), (4, 128, 64, 32), (1, 64, 64, 64)])
+def test_stride2_conv_both_paddings(engine, n, ci, co, hs):
+    """UNet Downsample (pad 1, stride 2) and VAE Downsample (pad (0,1,0,1), stride 2): TMA element strides on tc5."""
+    x, w = rnd(n, ci, hs, hs), rnd(co, ci, 3, 3, scale=(9 * ci) ** -0.5)
+    b = rnd(co, scale=0.1)
+    xh = nhwc(x)
+    xr, wr = xh.permute(0, 3, 1, 2).float(), w.to(H).float()
+    for asym in (False, True):
+        ref = F.conv2d(F.pad(xr, (0, 1, 0, 1)), wr, b, stride=2) if asym else F.conv2d(xr, wr, b, stride=2, padding=1)
+        ho = ref.shape[2]
+        out = torch.zeros(n * ho * ho, co, dtype=H, device=DEV)
+        ops.Gemm(ops.conv_taps([xh], pad_lo=0 if asym else 1), pack.pack_conv2d(w), out, n * ho * ho, mode=ops.ROWS_CONV2D,
+                 geom=dict(Ho=ho, Wo=ho, Hs=hs, Ws=hs, stride=2), bias=b, engine=engine)()
+        close(out.view(n, ho, ho, co).permute(0, 3, 1, 2), ref, name=f"stride2 asym={asym} {engine}")
+
+
+@pytest.mark.parametrize("engine", ["mma", "tc5"])
+@pytest.mark.parametrize("n,ci,co,hs", [(2, 64, 128, 16), (4, 128, 64, 8), (1, 64, 64, 32)])
+def test_upsample_conv_as_parity_convs(engine, n, ci, co, hs):
+    """nearest x2 + conv3x3 == four parity-class 2x2 convs with pre-summed taps, written through out_up."""
+    x, w = rnd(n, ci, hs, hs), rnd(co, ci, 3, 3, scale=(9 * ci) ** -0.5)
+    b = rnd(co, scale=0.1)
+    xh = nhwc(x)
+    ref = F.conv2d(F.interpolate(xh.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest"), w.to(H).float(), b, padding=1)
+    out = torch.zeros(n * 4 * hs * hs, co, dtype=H, device=DEV)
+    for (py, px), (Wt, shifts) in pack.pack_upconv_parity(w).items():
+        ops.Gemm([ops.SegSpec(xh, dy=sy, dx=sx) for sy, sx in shifts], Wt, out, n * hs * hs, mode=ops.ROWS_CONV2D,
+                 geom=dict(Ho=hs, Wo=hs, Hs=hs, Ws=hs, out_up=1, out_py=py, out_px=px), bias=b, engine=engine)()
+    # pre-summed fp16 taps add one more fp16 rounding of the weights: slightly wider tolerance
+    close(out.view(n, 2 * hs, 2 * hs, co).permute(0, 3, 1, 2), ref, rtol=4e-3, name=f"upconv parity {engine}")
