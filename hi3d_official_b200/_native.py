@@ -29,7 +29,8 @@ class GemmParams(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("mode", C.c_int32),
                 ("Ho", C.c_int32), ("Wo", C.c_int32), ("Hs", C.c_int32), ("Ws", C.c_int32),
                 ("stride", C.c_int32), ("ups", C.c_int32), ("T", C.c_int32),
-                ("out_up", C.c_int32), ("out_py", C.c_int32), ("out_px", C.c_int32), ("nseg", C.c_int32),
+                ("out_up", C.c_int32), ("out_py", C.c_int32), ("out_px", C.c_int32),
+                ("Tin", C.c_int32), ("t_off", C.c_int32), ("nseg", C.c_int32),
                 ("seg", Seg * MAX_SEGS),
                 ("W", C.c_void_p), ("bias", C.c_void_p), ("rowbias", C.c_void_p),
                 ("rb_div", C.c_int32), ("rb_mod", C.c_int32), ("rb_ld", C.c_int32), ("act", C.c_int32),
@@ -50,6 +51,11 @@ _SIGS = {
     "hi3d_groupnorm_ws_floats": (C.c_int64, [C.c_int]),
     "hi3d_groupnorm_silu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hi3d_groupnorm_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "hi3d_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_void_p]),
     "hi3d_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "hi3d_attention_d64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

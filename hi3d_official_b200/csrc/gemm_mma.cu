@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mma_kernel(const __grid_
       rb[i] = oy * p.stride;
       rc[i] = ox * p.stride;
     } else if (MODE == HI3D_ROWS_TEMPORAL) {
-      ra[i] = (mm / HW) % p.T;
-      rb[i] = rc[i] = 0;
+      const int fr = mm / HW;                 // output frame index (b * T + t)
+      ra[i] = fr % p.T + p.t_off;             // frame position inside the source clip
+      rb[i] = (fr / p.T) * (p.Tin > 0 ? p.Tin : p.T);   // first source frame of this clip
+      rc[i] = mm - fr * HW;                   // pixel
     } else {
       ra[i] = rb[i] = rc[i] = 0;
     }
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mma_kernel(const __grid_
         pix = (long long)(ra[i] + (iy >> p.ups)) * p.Ws + (ix >> p.ups);
       } else if (MODE == HI3D_ROWS_TEMPORAL) {
         int tt = ra[i] + sg.dt;
-        v = v && ((unsigned)tt < (unsigned)p.T);
-        pix = (long long)(m0 + r) + (long long)sg.dt * HW;
+        v = v && ((unsigned)tt < (unsigned)(p.Tin > 0 ? p.Tin : p.T));
+        pix = (long long)(rb[i] + tt) * HW + rc[i];
       } else {
         pix = m0 + r;
       }
@@ -326,7 +328,8 @@ int validate_gemm(const hi3d_gemm_params* p, const char* who) {
     set_error("%s: out_up is a CONV2D option", who);
     return -2;
   } else if (p->mode == HI3D_ROWS_TEMPORAL) {
-    if (p->T <= 0 || p->Ho * p->Wo <= 0 || (p->M % (p->T * p->Ho * p->Wo))) {
+    if (p->T <= 0 || p->Ho * p->Wo <= 0 || (p->M % (p->T * p->Ho * p->Wo)) || p->Tin < 0 || p->t_off < 0 ||
+        (p->Tin > 0 && p->t_off + p->T > p->Tin)) {
       set_error("%s: bad temporal geometry T=%d HW=%d M=%d", who, p->T, p->Ho * p->Wo, p->M);
       return -2;
     }

@@ -54,6 +54,7 @@ struct T5Params {
   int tiles_x, tiles_y;  // tiles along W and H (CONV2D) / along HW and T (TEMPORAL)
   int cstride;           // CONV2D input stride (1 | 2): TMA element strides, box origin = tile origin * cstride + tap
   int out_up, out_py, out_px;   // parity-class output mapping (see hi3d_gemm_params::out_up)
+  int t_off;                    // TEMPORAL: frame offset of output frame 0 inside the (haloed) source clip
   // epilogue
   const float* bias;
   const __half* rowbias;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           else if (p.mode == HI3D_ROWS_CONV2D)
             tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
           else
-            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0, o.y0 + sg.dt, o.z0);
+            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0, o.y0 + p.t_off + sg.dt, o.z0);
           tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
           so += T5_BK;
           if (so >= sg.C) { si++; so = 0; }
@@ -430,6 +431,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.M = p->M; tp.N = p->N; tp.K = p->K; tp.mode = p->mode; tp.nseg = p->nseg;
   tp.cstride = (p->mode == HI3D_ROWS_CONV2D) ? p->stride : 1;
   tp.out_up = p->out_up; tp.out_py = p->out_py; tp.out_px = p->out_px;
+  tp.t_off = p->t_off;
   int m_tiles = 0;
   bool ok = (p->N >= 32) && (p->N % 8 == 0);
   // the vectorised epilogue needs 16-byte aligned rows / bias
@@ -522,7 +524,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
       cuuint32_t est[4] = {1, cs, cs, 1};
       if (encode_map(&tp.amap[j], srcs[j], 4, dims, str, box, est)) return -1;
     } else {
-      const cuuint64_t HW = (cuuint64_t)tp.Wo, T = (cuuint64_t)tp.Ho;
+      const cuuint64_t HW = (cuuint64_t)tp.Wo, T = (cuuint64_t)(p->Tin > 0 ? p->Tin : tp.Ho);   // source frames per clip
       cuuint64_t dims[4] = {ld, HW, T, (cuuint64_t)tp.Nimg};
       cuuint64_t str[3] = {ld * 2, ld * 2 * HW, ld * 2 * HW * T};
       cuuint32_t box[4] = {64, (cuuint32_t)tp.tw, (cuuint32_t)tp.th, 1};

@@ -85,11 +85,10 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   if (tid < GN_GROUPS * 2) ws[((long long)n * GN_MAX_CHUNKS + chunk) * (GN_GROUPS * 2) + tid] = sg[tid];
 }
 
-// ---- pass 1b: combine the chunk partials of one sample into (mean, rstd) per group -------------------------
-// grid (n_samples), 1024 threads; result at fin[n][32][2].
+// ---- pass 1b: combine the chunk partials of one sample into (sum, sum of squares) per group ----------------
+// grid (n_samples), 1024 threads; result at fin[n][32][2].  (Frame-sharded runs all-reduce `fin` across ranks here.)
 __global__ void __launch_bounds__(1024)
-gn_finalize_kernel(const float* __restrict__ ws, int nchunks, long long rows_per_sample, int cpg, float eps,
-                   float* __restrict__ fin) {
+gn_finalize_kernel(const float* __restrict__ ws, int nchunks, float* __restrict__ fin) {
   __shared__ float stot[GN_GROUPS * 2];
   const int tid = threadIdx.x, n = blockIdx.x;
   if (tid < GN_GROUPS * 2) stot[tid] = 0.f;
@@ -107,28 +106,25 @@ gn_finalize_kernel(const float* __restrict__ ws, int nchunks, long long rows_per
   for (; c < nchunks; c += 16) a0 += w[c * (GN_GROUPS * 2) + (tid & 63)];
   atomicAdd(&stot[tid & 63], (a0 + a1) + (a2 + a3));
   __syncthreads();
-  if (tid < GN_GROUPS) {
-    const double cnt = (double)rows_per_sample * (double)cpg;
-    const double mean = (double)stot[2 * tid] / cnt;
-    double var = (double)stot[2 * tid + 1] / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    fin[(long long)n * (GN_GROUPS * 2) + 2 * tid] = (float)mean;
-    fin[(long long)n * (GN_GROUPS * 2) + 2 * tid + 1] = (float)(1.0 / sqrt(var + (double)eps));
-  }
+  if (tid < GN_GROUPS * 2) fin[(long long)n * (GN_GROUPS * 2) + tid] = stot[tid];
 }
 
 // ---- pass 2: y = [silu]((x - mean) * rstd * gamma + beta) ------------------------------------------
 // grid (row_slabs, n_samples), blockDim = RL * CV.
 __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
-                long long rows_per_cta, const float* __restrict__ fin, const float* __restrict__ gamma,
-                const float* __restrict__ beta, int apply_silu, __half* __restrict__ y) {
+                long long rows_per_cta, const float* __restrict__ fin, double count, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int apply_silu, __half* __restrict__ y,
+                long long y_sample_rows, long long y_row_off) {
   __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
   const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
   const int tid = threadIdx.x, n = blockIdx.y;
-  if (tid < GN_GROUPS) {
-    smean[tid] = fin[(long long)n * (GN_GROUPS * 2) + 2 * tid];
-    srstd[tid] = fin[(long long)n * (GN_GROUPS * 2) + 2 * tid + 1];
+  if (tid < GN_GROUPS) {      // `count` = elements per (sample, group) over ALL ranks
+    const double mean = (double)fin[(long long)n * (GN_GROUPS * 2) + 2 * tid] / count;
+    double var = (double)fin[(long long)n * (GN_GROUPS * 2) + 2 * tid + 1] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    smean[tid] = (float)mean;
+    srstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
   const int cv = tid % CV, rl = tid / CV, RL = blockDim.x / CV;
@@ -145,7 +141,7 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   if (c0 < C1) { base = x1 + c0; ld = C1; } else { base = x2 + (c0 - C1); ld = C2; }
   const long long srow0 = (long long)n * rows_per_sample;
   base += srow0 * ld;
-  __half* yb = y + srow0 * C + c0;
+  __half* yb = y + ((long long)n * y_sample_rows + y_row_off) * C + c0;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > rows_per_sample) r1 = rows_per_sample;
@@ -315,24 +311,28 @@ extern "C" int64_t hi3d_groupnorm_ws_floats(int n_samples) {
   return (int64_t)n_samples * (GN_MAX_CHUNKS + 1) * GN_GROUPS * 2;     // chunk partials + final (mean, rstd)
 }
 
-extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples,
-                                   int64_t rows_per_sample, const float* gamma, const float* beta, float eps,
-                                   int apply_silu, void* y, float* ws, void* stream) {
-  if (!x2) C2 = 0;
+static int gn_check(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample, const char* who) {
   const int C = C1 + C2;
-  if (!x1 || !y || !ws || !gamma || !beta || n_samples <= 0 || rows_per_sample <= 0 || C1 <= 0 || (C1 % 8) || (C2 % 8) ||
-      (C % GN_GROUPS) || C > 4096 || ((uintptr_t)x1 & 15) || ((uintptr_t)y & 15) || (x2 && ((uintptr_t)x2 & 15)) ||
-      n_samples > 65535) {
-    set_error("hi3d_groupnorm_silu: bad arguments (C1=%d C2=%d n=%d rows=%lld)", C1, C2, n_samples,
-              (long long)rows_per_sample);
+  if (!x1 || n_samples <= 0 || rows_per_sample <= 0 || C1 <= 0 || (C1 % 8) || (C2 % 8) || (C % GN_GROUPS) || C > 4096 ||
+      ((uintptr_t)x1 & 15) || (x2 && ((uintptr_t)x2 & 15)) || n_samples > 65535) {
+    set_error("%s: bad arguments (C1=%d C2=%d n=%d rows=%lld)", who, C1, C2, n_samples, (long long)rows_per_sample);
     return -2;
   }
+  return 0;
+}
+
+// (sum, sum of squares) per (sample, group) of the LOCAL rows -> sums[n_samples][32][2] (fp32)
+extern "C" int hi3d_groupnorm_sums(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
+                                   float* sums, float* ws, void* stream) {
+  if (!x2) C2 = 0;
+  int rc = gn_check(x1, C1, x2, C2, n_samples, rows_per_sample, "hi3d_groupnorm_sums");
+  if (rc) return rc;
+  if (!sums || !ws) { set_error("hi3d_groupnorm_sums: null output / workspace"); return -2; }
   cudaStream_t st = (cudaStream_t)stream;
-  const int CV = C / 8;
+  const int C = C1 + C2, CV = C / 8;
   const int threads = (512 / CV) * CV;
   const int RL = threads / CV;
   const long long min_rows = (long long)RL * GN_UNROLL;     // one unrolled sweep per thread at least
-  // ---- stats: ~4 waves of CTAs, bounded by the workspace layout and by a minimum of work per CTA
   long long chunks = (GN_TARGET_CTAS + n_samples - 1) / n_samples;
   const long long max_by_rows = (rows_per_sample + min_rows - 1) / min_rows;
   if (chunks > max_by_rows) chunks = max_by_rows;
@@ -343,23 +343,54 @@ extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C
   chunks = (rows_per_sample + rpc - 1) / rpc;
   gn_stats_kernel<<<dim3((unsigned)chunks, n_samples), threads, 0, st>>>((const __half*)x1, C1, (const __half*)x2, C2,
                                                                         rows_per_sample, rpc, ws);
-  int rc = check_launch("hi3d_groupnorm_silu(stats)");
+  rc = check_launch("hi3d_groupnorm_sums(stats)");
   if (rc) return rc;
-  float* fin = ws + (long long)n_samples * GN_MAX_CHUNKS * GN_GROUPS * 2;
-  gn_finalize_kernel<<<n_samples, 1024, 0, st>>>(ws, (int)chunks, rows_per_sample, C / GN_GROUPS, eps, fin);
-  rc = check_launch("hi3d_groupnorm_silu(finalize)");
+  gn_finalize_kernel<<<n_samples, 1024, 0, st>>>(ws, (int)chunks, sums);
+  return check_launch("hi3d_groupnorm_sums(finalize)");
+}
+
+// y = [silu]((x - mean) * rstd * gamma + beta) with mean / rstd from `sums` over `count_rows` rows per sample
+// (count_rows = rows_per_sample for a single GPU, the GLOBAL row count when the sums were all-reduced over ranks).
+// Sample n of y starts at row n * y_sample_rows + y_row_off (haloed temporal buffers); 0, 0 -> dense like x.
+extern "C" int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
+                                    const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
+                                    int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* stream) {
+  if (!x2) C2 = 0;
+  int rc = gn_check(x1, C1, x2, C2, n_samples, rows_per_sample, "hi3d_groupnorm_apply");
   if (rc) return rc;
-  // ---- apply: same sizing rule (each CTA also re-reduces `chunks` x 64 partials, a few KB)
+  if (!sums || !gamma || !beta || !y || ((uintptr_t)y & 15) || count_rows <= 0) {
+    set_error("hi3d_groupnorm_apply: bad arguments");
+    return -2;
+  }
+  if (y_sample_rows <= 0) { y_sample_rows = rows_per_sample; y_row_off = 0; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = C1 + C2, CV = C / 8;
+  const int threads = (512 / CV) * CV;
+  const int RL = threads / CV;
+  const long long min_rows = (long long)RL * GN_UNROLL;
+  const long long max_by_rows = (rows_per_sample + min_rows - 1) / min_rows;
   long long slabs = (GN_TARGET_CTAS + n_samples - 1) / n_samples;
   if (slabs > max_by_rows) slabs = max_by_rows;
   if (slabs < 1) slabs = 1;
   long long rows_per_cta = (rows_per_sample + slabs - 1) / slabs;
   rows_per_cta = (rows_per_cta + RL - 1) / RL * RL;
   slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
-  if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_silu: too many slabs"); return -2; }
+  if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_apply: too many slabs"); return -2; }
   gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
-      (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, fin, gamma, beta, apply_silu, (__half*)y);
-  return check_launch("hi3d_groupnorm_silu(apply)");
+      (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, sums,
+      (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off);
+  return check_launch("hi3d_groupnorm_apply");
+}
+
+extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples,
+                                   int64_t rows_per_sample, const float* gamma, const float* beta, float eps,
+                                   int apply_silu, void* y, float* ws, void* stream) {
+  if (!ws) { set_error("hi3d_groupnorm_silu: null workspace"); return -2; }
+  float* sums = ws + (long long)n_samples * GN_MAX_CHUNKS * GN_GROUPS * 2;
+  int rc = hi3d_groupnorm_sums(x1, C1, x2, C2, n_samples, rows_per_sample, sums, ws, stream);
+  if (rc) return rc;
+  return hi3d_groupnorm_apply(x1, C1, x2, C2, n_samples, rows_per_sample, sums, rows_per_sample, gamma, beta, eps, apply_silu,
+                              y, 0, 0, stream);
 }
 
 extern "C" int hi3d_layernorm(const void* x, const void* addvec, int add_div, int add_mod, int64_t M, int C,

@@ -84,6 +84,7 @@ class Gemm:
         p.Hs, p.Ws = g.get("Hs", p.Ho), g.get("Ws", p.Wo)
         p.stride, p.ups, p.T = g.get("stride", 1), g.get("ups", 0), g.get("T", 1)
         p.out_up, p.out_py, p.out_px = g.get("out_up", 0), g.get("out_py", 0), g.get("out_px", 0)
+        p.Tin, p.t_off = g.get("Tin", 0), g.get("t_off", 0)
         p.nseg = len(segs)
         for i, s in enumerate(segs):
             p.seg[i].src, p.seg[i].ld, p.seg[i].c_off, p.seg[i].C = s.src.data_ptr(), s.ld, s.c_off, s.C
@@ -141,6 +142,25 @@ def groupnorm_silu(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int,
     N.check(N.load().hi3d_groupnorm_silu(x1.data_ptr(), x1.shape[-1], _ptr(x2), c2, n_samples, rows_per_sample,
                                          gamma.data_ptr(), beta.data_ptr(), eps, int(silu), y.data_ptr(),
                                          ws.data_ptr(), _stream()), "hi3d_groupnorm_silu")
+
+
+def groupnorm_sums(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int, rows_per_sample: int, sums: torch.Tensor,
+                   ws: torch.Tensor):
+    """Local (sum, sumsq) per (sample, group) -> sums fp32 [n_samples, 32, 2] (all-reduced by the caller when sharded)."""
+    _chk16(x1, "x1"); _chk32(sums, "sums")
+    c2 = 0 if x2 is None else x2.shape[-1]
+    N.check(N.load().hi3d_groupnorm_sums(x1.data_ptr(), x1.shape[-1], _ptr(x2), c2, n_samples, rows_per_sample,
+                                         sums.data_ptr(), ws.data_ptr(), _stream()), "hi3d_groupnorm_sums")
+
+
+def groupnorm_apply(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int, rows_per_sample: int, sums: torch.Tensor,
+                    count_rows: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, y: torch.Tensor,
+                    y_sample_rows: int = 0, y_row_off: int = 0):
+    _chk16(x1, "x1"); _chk16(y, "y"); _chk32(sums, "sums"); _chk32(gamma, "gamma"); _chk32(beta, "beta")
+    c2 = 0 if x2 is None else x2.shape[-1]
+    N.check(N.load().hi3d_groupnorm_apply(x1.data_ptr(), x1.shape[-1], _ptr(x2), c2, n_samples, rows_per_sample,
+                                          sums.data_ptr(), count_rows, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
+                                          y.data_ptr(), y_sample_rows, y_row_off, _stream()), "hi3d_groupnorm_apply")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, M: int,

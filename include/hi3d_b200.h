@@ -73,6 +73,9 @@ typedef struct {
                                (2y + out_py, 2x + out_px): one parity class of nearest-x2 + conv3x3, which is a 2x2
                                conv on the source grid with pre-summed taps (4 launches, 4/9 of the FLOPs)       */
   int32_t out_py, out_px;
+  int32_t Tin, t_off;       /* TEMPORAL: frames per clip in the SOURCE tensors and frame offset of output frame 0 in it
+                               (0, 0 -> Tin = T).  Frame-sharded runs read a haloed [B, T_local + 2, HW, C] buffer:
+                               Tin = T + 2, t_off = 1; taps that fall outside [0, Tin) read zeros.            */
   int32_t nseg;
   hi3d_seg seg[HI3D_MAX_SEGS];
   const void* W;            /* fp16 [N, K], K contiguous, K ordered as the segments                    */
@@ -110,6 +113,16 @@ int64_t hi3d_groupnorm_ws_floats(int n_samples);
 int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
                         const float* gamma, const float* beta, float eps, int apply_silu, void* y, float* ws,
                         void* stream);
+
+/* The two halves of hi3d_groupnorm_silu, exposed for frame-sharded runs where the temporal ResBlock's GroupNorm reduces
+ * over (C/32, T, H, W) with T split over GPUs: `sums` fp32 [n_samples, 32, 2] = (sum, sum of squares) of the
+ * local rows; the host all-reduces them over ranks and passes count_rows = the GLOBAL rows per sample.  y may be a
+ * haloed buffer: sample n starts at row n * y_sample_rows + y_row_off (0, 0 = dense). */
+int hi3d_groupnorm_sums(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample, float* sums,
+                        float* ws, void* stream);
+int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
+                         const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
+                         int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* stream);
 
 /* LayerNorm over the last dim C (<= 2560, multiple of 8) of [M, C] fp16 (+ optional broadcast add before the norm:
  * x + addvec[((m / add_div) % add_mod), :], the `x_mix = x + emb` of video_attention.py:286-287).
