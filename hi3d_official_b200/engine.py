@@ -127,8 +127,8 @@ class DiffusionEngine(nn.Module):
         return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
 
     # -- the pipelines' denoiser closure as a fusable binding ---------------------------------------------------------------
-    def bind_denoiser(self, **additional_model_inputs) -> FusedDenoiser:
-        return FusedDenoiser(self.denoiser, self.model, **additional_model_inputs)
+    def bind_denoiser(self, shard=None, **additional_model_inputs) -> FusedDenoiser:
+        return FusedDenoiser(self.denoiser, self.model, shard=shard, **additional_model_inputs)
 
 
 class VideoLDM(DiffusionEngine):
@@ -157,9 +157,11 @@ class VideoLDM(DiffusionEngine):
 
     # ---- hot loop of pipeline_i2v_eval_v01.py:62-98 (after conditioning) ------------------------------------------------------
     @torch.no_grad()
-    def sample_stage1(self, c: Dict, uc: Dict, randn: torch.Tensor, decode: bool = True):
+    def sample_stage1(self, c: Dict, uc: Dict, randn: torch.Tensor, decode: bool = True, shard=None):
+        """shard = (rank, world): `randn` and c/uc['concat'] hold only this rank's frames (frame-sharded video); the
+        returned latents / decoded frames are this rank's frames too."""
         T = self.num_samples
-        den = self.bind_denoiser(image_only_indicator=None, num_video_frames=T)
+        den = self.bind_denoiser(shard=shard, image_only_indicator=None, num_video_frames=T)
         samples = self.sampler(den, randn, cond=c, uc=uc)
         if not decode:
             return samples
@@ -189,19 +191,20 @@ class VideoLDMStage2(VideoLDM):
     # ---- hot loop of pipeline_i2v_eval_v02.py:86-137 ---------------------------------------------------------------------------
     @torch.no_grad()
     def sample_stage2(self, c: Dict, uc: Dict, init_latents: torch.Tensor, z: torch.Tensor, decode: bool = True,
-                      alpha_pow: float = 40.0):
-        """init_latents ~ N(0,1) (T,4,h,w) fp32; z = encode_first_stage(low-res frames) (T,4,h,w)."""
+                      alpha_pow: float = 40.0, shard=None):
+        """init_latents ~ N(0,1) (T,4,h,w) fp32; z = encode_first_stage(low-res frames) (T,4,h,w).
+        shard = (rank, world): all per-frame tensors hold only this rank's frames."""
         from . import ops
         smp = self.sampler
         T = self.num_samples
         sigmas = smp.discretization(smp.num_steps, device="cpu").to(init_latents.device)
         num_sigmas = len(sigmas)
         sig_host = sigmas.tolist()
-        s_in = init_latents.new_ones([T])
+        s_in = init_latents.new_ones([init_latents.shape[0]])
         latents = (init_latents * math.sqrt(1.0 + sig_host[0] ** 2.0)).contiguous()
         init_latents = init_latents.float().contiguous()
         z = z.float().contiguous()
-        den = self.bind_denoiser(image_only_indicator=None, num_video_frames=T)
+        den = self.bind_denoiser(shard=shard, image_only_indicator=None, num_video_frames=T)
         for i in smp.get_sigma_gen(num_sigmas):
             alpha = math.pow(0.5 * (1 + math.cos(i * 1.0 / smp.num_steps)), alpha_pow)
             ops.renoise_blend(latents, init_latents, z, alpha, sig_host[i])           # v02:131-132

@@ -192,8 +192,12 @@ class FusedDenoiser:
     (pipeline_i2v_eval_v01.py:85-88) as an inspectable object, so the sampler can run the fused B200 step.
     Calling it behaves exactly like the closure (generic path)."""
 
-    def __init__(self, denoiser: Denoiser, network: nn.Module, **additional_model_inputs):
+    def __init__(self, denoiser: Denoiser, network: nn.Module, shard: Optional[Tuple[int, int]] = None,
+                 **additional_model_inputs):
         self.denoiser, self.network, self.kwargs = denoiser, network, additional_model_inputs
+        # shard = (rank, world): the caller passes only this rank's frames of x / cond['concat'] (frame sharding over
+        # GPUs, SURVEY 8e); num_video_frames stays the GLOBAL frame count
+        self.shard = None if shard is None or shard[1] == 1 else (int(shard[0]), int(shard[1]))
 
     def __call__(self, input, sigma, c):
         return self.denoiser(self.network, input, sigma, c, **self.kwargs)
@@ -206,14 +210,15 @@ class FusedDenoiser:
 class _FusedState:
     """Per-(shape) fused step executor bound to one VideoUNet launch plan."""
 
-    def __init__(self, unet: VideoUNet, F_: int, H: int, W: int, T: int, scale: torch.Tensor):
-        self.plan = unet.get_plan(2 * F_, H, W, T)
+    def __init__(self, unet: VideoUNet, F_: int, H: int, W: int, T: int, scale: torch.Tensor, shard=None):
+        self.plan = unet.get_plan(2 * F_, H, W, T, shard=shard)
         dev = unet.device
         self.scale = scale.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
         self.key = None
         self.cc = self.cuc = None
         # CUDA-graph replay of the whole step (pre -> ~750 launches -> post): static I/O buffers + one graph
-        self.use_graph = os.environ.get("HI3D_CUDA_GRAPH", "1") != "0"
+        # (not with frame sharding: the NCCL exchanges are issued eagerly)
+        self.use_graph = os.environ.get("HI3D_CUDA_GRAPH", "1") != "0" and shard is None
         self._graph = None
         self._gx = torch.zeros(F_, 4, H, W, dtype=torch.float32, device=dev)
         self._gxo = torch.zeros_like(self._gx)
@@ -343,13 +348,24 @@ class EDMSampler(SingleStepDiffusionSampler):
             return None
         unet = denoiser.network.diffusion_model
         T = int(denoiser.kwargs["num_video_frames"])
-        if T != self.guider.num_frames or x.shape[0] % T:
+        if T != self.guider.num_frames:
+            return None
+        shard = denoiser.shard
+        scale = self.guider.scale.reshape(-1)
+        if shard is not None:             # this rank holds frames [rank*Tl, (rank+1)*Tl) of every clip
+            if T % shard[1]:
+                raise ValueError(f"{T} frames cannot be sharded over {shard[1]} ranks")
+            Tl = T // shard[1]
+            scale = scale[shard[0] * Tl:(shard[0] + 1) * Tl]
+            T = Tl
+        if x.shape[0] % T:
             return None
         F_, _, H, W = x.shape
-        key = (id(unet), F_, H, W, T, unet.engine)
+        key = (id(unet), F_, H, W, T, unet.engine, shard)
+        pkey = (2 * F_, H, W, T, unet.engine) if shard is None else (2 * F_, H, W, T, unet.engine, shard)
         st = self._fused.get(key)
-        if st is None or st.plan is not unet._plans.get((2 * F_, H, W, T, unet.engine)):
-            st = self._fused[key] = _FusedState(unet, F_, H, W, T, self.guider.scale)
+        if st is None or st.plan is not unet._plans.get(pkey):
+            st = self._fused[key] = _FusedState(unet, F_, H, W, T, scale, shard)
         ck = _FusedState.cond_key(cond, uc)
         if refresh or st.key != ck:
             st.set_conditioning(cond, uc)

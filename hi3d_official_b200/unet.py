@@ -203,10 +203,12 @@ class VideoUNet(nn.Module):
         return P
 
     # ---- plans --------------------------------------------------------------------------------------------
-    def get_plan(self, N: int, H: int, W: int, T: int) -> "_Plan":
-        key = (N, H, W, T, self.engine)
+    def get_plan(self, N: int, H: int, W: int, T: int, shard: Optional[Tuple[int, int]] = None) -> "_Plan":
+        """shard = (rank, world): frame-sharded plan -- N = B * T local samples, this rank owns frames
+        [rank*T, (rank+1)*T) of clips of world*T frames (needs an initialised torch.distributed group)."""
+        key = (N, H, W, T, self.engine) if shard is None else (N, H, W, T, self.engine, tuple(shard))
         if key not in self._plans:
-            self._plans[key] = _Plan(self, N, H, W, T)
+            self._plans[key] = _Plan(self, N, H, W, T, shard=shard)
         return self._plans[key]
 
     # ---- reference-compatible forward ------------------------------------------------------------------------
@@ -237,10 +239,13 @@ class VideoUNet(nn.Module):
 class _Plan:
     """Flat launch list for one (N, H, W, T): buffers, pre-baked GEMM parameter blocks, per-step entry points."""
 
-    def __init__(self, net: VideoUNet, N: int, H: int, W: int, T: int):
+    def __init__(self, net: VideoUNet, N: int, H: int, W: int, T: int, shard: Optional[Tuple[int, int]] = None):
+        self.shard = None if shard is None or shard[1] == 1 else (int(shard[0]), int(shard[1]))
+        self.rank, self.world = self.shard if self.shard else (0, 1)
+        self.Tg = T * self.world                     # frames per clip over all ranks
         if N % T:
             raise ValueError(f"batch {N} is not a multiple of num_video_frames {T}")
-        if T > 16:
+        if T * (1 if shard is None else int(shard[1])) > 16:
             raise NotImplementedError("temporal attention kernel supports T <= 16 frames")
         nlev = len(net.cfg.channel_mult)
         if H % (1 << (nlev - 1)) or W % (1 << (nlev - 1)):
@@ -272,7 +277,8 @@ class _Plan:
         self.ctx_in = torch.zeros(N, cfg.context_dim, dtype=F16, device=dev)
         self.ctx_first = torch.zeros(self.B, cfg.context_dim, dtype=F16, device=dev)
         self.gn_ws = ops.groupnorm_ws(N, dev)
-        self.frame_idx = torch.arange(T, dtype=torch.float32, device=dev)
+        self.frame_idx = torch.arange(T, dtype=torch.float32, device=dev) + float(self.rank * T)   # global frame ids
+        self.gn_sums = torch.zeros(self.B, 32, 2, dtype=torch.float32, device=dev)               # sharded temporal GN
         self._cond_key = None
         self._compile()
 
@@ -451,18 +457,67 @@ class _Plan:
         # -- temporal half: statistics over (T, H, W) per clip, 3-tap conv along frames
         q = n + "time_stack."
         g3, b3 = P[q + "gn1"]
-        self._call(bl, lambda: ops.groupnorm_silu(xs.t, None, B, T * HW, g3, b3, 1e-5, True, g_mid.t, ws),
-                   kind="groupnorm", bytes=6.0 * M * cout)
-        geo = dict(Ho=HW, Wo=1, T=T)
-        emb2 = self._emb_slice(q)
-        self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv1"][0], hbuf, M, mode=ops.ROWS_TEMPORAL, geom=geo,
-                   bias=P[q + "conv1"][1], rowbias=emb2, rb_div=HW, rb_mod=N)
         g4, b4 = P[q + "gn2"]
-        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, B, T * HW, g4, b4, 1e-5, True, g_mid.t, ws),
-                   kind="groupnorm", bytes=6.0 * M * cout)
-        # x_t = xs + conv(...);  out = alpha*xs + (1-alpha)*x_t   (util.py:358-369)
-        self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv2"][0], out, M, mode=ops.ROWS_TEMPORAL, geom=geo,
-                   bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"])
+        emb2 = self._emb_slice(q)
+        if self.shard is None:
+            self._call(bl, lambda: ops.groupnorm_silu(xs.t, None, B, T * HW, g3, b3, 1e-5, True, g_mid.t, ws),
+                       kind="groupnorm", bytes=6.0 * M * cout)
+            geo = dict(Ho=HW, Wo=1, T=T)
+            self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv1"][0], hbuf, M, mode=ops.ROWS_TEMPORAL, geom=geo,
+                       bias=P[q + "conv1"][1], rowbias=emb2, rb_div=HW, rb_mod=N)
+            self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, B, T * HW, g4, b4, 1e-5, True, g_mid.t, ws),
+                       kind="groupnorm", bytes=6.0 * M * cout)
+            # x_t = xs + conv(...);  out = alpha*xs + (1-alpha)*x_t   (util.py:358-369)
+            self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv2"][0], out, M, mode=ops.ROWS_TEMPORAL, geom=geo,
+                       bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"])
+            return
+        # frames sharded over ranks: (sum, sumsq) all-reduce for the (T,H,W) statistics, GN output
+        # written into a haloed [B, T+2, HW, C] buffer, one-frame halo exchange, 3-tap conv over the haloed source.
+        gh = A.want("ghalo", B * (T + 2) * HW, cout)
+        geo = dict(Ho=HW, Wo=1, T=T, Tin=T + 2, t_off=1)
+        for src, (gg, bb), wkey, dst, extra in (
+                (xs, (g3, b3), "conv1", hbuf, dict(rowbias=emb2, rb_div=HW, rb_mod=N)),
+                (hbuf, (g4, b4), "conv2", out, dict(residual=xs, blend_x=xs, alpha=P[n + "alpha"]))):
+            self._call(bl, lambda src=src: ops.groupnorm_sums(src.t, None, B, T * HW, self.gn_sums, ws), kind="groupnorm",
+                       bytes=2.0 * M * cout)
+            self._call(bl, lambda: self._allreduce(self.gn_sums), kind="nccl")
+            self._call(bl, lambda src=src, gg=gg, bb=bb: ops.groupnorm_apply(
+                src.t, None, B, T * HW, self.gn_sums, self.Tg * HW, gg, bb, 1e-5, True, gh.t, (T + 2) * HW, HW),
+                kind="groupnorm", bytes=4.0 * M * cout)
+            self._call(bl, lambda: self._halo_exchange(gh.t.view(B, T + 2, HW * cout)), kind="nccl")
+            self._gemm(bl, lambda: ops.temporal_taps(gh.t), P[q + wkey][0], dst, M, mode=ops.ROWS_TEMPORAL, geom=geo,
+                       bias=P[q + wkey][1], **extra)
+
+    # ---- frame-sharding collectives (torch.distributed / NCCL on the current stream) -----------------------------------
+    def _allreduce(self, t: torch.Tensor):
+        import torch.distributed as dist
+        dist.all_reduce(t)
+
+    def _halo_exchange(self, g: torch.Tensor):
+        """g: [B, T+2, HW*C] haloed GN output; frame 0 <- last frame of rank-1, frame T+1 <- first frame of rank+1,
+        zeros at the clip boundaries (the Conv3d zero padding at t = -1 and t = T, openaimodel.py:252-261)."""
+        import torch.distributed as dist
+        r, R, T = self.rank, self.world, self.T
+        ops_ = []
+        for b in range(g.shape[0]):
+            if r > 0:
+                ops_ += [dist.P2POp(dist.isend, g[b, 1], r - 1), dist.P2POp(dist.irecv, g[b, 0], r - 1)]
+            else:
+                g[b, 0].zero_()
+            if r + 1 < R:
+                ops_ += [dist.P2POp(dist.isend, g[b, T], r + 1), dist.P2POp(dist.irecv, g[b, T + 1], r + 1)]
+            else:
+                g[b, T + 1].zero_()
+        for wk in dist.batch_isend_irecv(ops_):
+            wk.wait()
+
+    def _gather_frames(self, local: torch.Tensor, full: torch.Tensor, rows_per_clip_local: int):
+        """local [B * T*HW, X] -> full [B * Tg*HW, X] (frame order) : one all-gather per clip (the K/V all-gather
+        before each temporal-attention block)."""
+        import torch.distributed as dist
+        n = rows_per_clip_local
+        for b in range(self.B):
+            dist.all_gather_into_tensor(full[b * n * self.world:(b + 1) * n * self.world], local[b * n:(b + 1) * n])
 
     def _transformer(self, L: Layer, x: LazyBuf, out: LazyBuf, h: int, w: int):
         """SpatialVideoTransformer.forward (video_attention.py:230-301), see module docstring for the folds."""
@@ -519,8 +574,21 @@ class _Plan:
                        residual=t2, rowbias=emb_t, rb_div=HW, rb_mod=T)
             self._ln(bl, u0, P[qt + "norm1"], ln, M)
             self._gemm(bl, lambda: [ops.SegSpec(ln.t)], P[qt + "qkv"], qkv, M)
-            self._call(bl, lambda: ops.temporal_attention_d64(qkv.t, B, T, HW, heads, att.t), kind="temporal_attention",
-                       flops=4.0 * N * HW * T * C, bytes=8.0 * M * C)
+            if self.shard is None:
+                self._call(bl, lambda: ops.temporal_attention_d64(qkv.t, B, T, HW, heads, att.t), kind="temporal_attention",
+                           flops=4.0 * N * HW * T * C, bytes=8.0 * M * C)
+            else:
+                # all-gather q|k|v rows of every rank (frame order), attend over all Tg frames, keep the local frames
+                Tg, r = self.Tg, self.rank
+                qkv_f, att_f = A.want("qkv_full", B * Tg * HW, 3 * C), A.want("att_full", B * Tg * HW, C)
+                self._call(bl, lambda: self._gather_frames(qkv.t, qkv_f.t, T * HW), kind="nccl")
+                self._call(bl, lambda: ops.temporal_attention_d64(qkv_f.t, B, Tg, HW, heads, att_f.t),
+                           kind="temporal_attention", flops=4.0 * B * Tg * HW * Tg * C, bytes=8.0 * B * Tg * HW * C)
+
+                def keep_local(att=att, att_f=att_f):
+                    for b in range(B):
+                        att.t[b * T * HW:(b + 1) * T * HW].copy_(att_f.t[(b * Tg + r * T) * HW:(b * Tg + (r + 1) * T) * HW])
+                self._call(bl, keep_local, kind="copy")
             self.flops += 4.0 * N * HW * T * C
             self._gemm(bl, lambda: [ops.SegSpec(att.t)], P[qt + "to_out"][0], t1, M, bias=P[qt + "to_out"][1],
                        residual=u0, rowbias=r_t, rb_div=T * HW, rb_mod=B)
