@@ -103,11 +103,18 @@ def to_cond(dev_t):
     return c, uc
 
 
-def run_video(model, stage: int, dev_t):
+def run_video(model, stage: int, dev_t, shard=None):
     c, uc = to_cond(dev_t)
     if stage == 1:
-        return model.sample_stage1(c, uc, dev_t["randn"].clone())
-    return model.sample_stage2(c, uc, dev_t["randn"].clone(), dev_t["z"])
+        return model.sample_stage1(c, uc, dev_t["randn"].clone(), shard=shard)
+    return model.sample_stage2(c, uc, dev_t["randn"].clone(), dev_t["z"], shard=shard)
+
+
+def shard_frames(t: dict, rank: int, world: int) -> dict:
+    """This rank's frames of the per-frame tensors (BASELINE configs[3]: one video, frames sharded over GPUs)."""
+    tl = T_FRAMES // world
+    sl = slice(rank * tl, (rank + 1) * tl)
+    return {k: (v[sl].contiguous() if v.shape[0] == T_FRAMES else v) for k, v in t.items()}
 
 
 def kernel_breakdown(model, stage: int, dev_t, peaks):
@@ -220,6 +227,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--engine", default=os.environ.get("HI3D_ENGINE", "tc5"), choices=("mma", "tc5"))
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--shard", default="videos", choices=("videos", "frames"),
+                    help="N > 1: 'videos' = one video per GPU (weak scaling, default); 'frames' = ONE video with its 16 "
+                         "frames sharded over the GPUs (strong scaling; K/V all-gather + halo + GN all-reduce per layer)")
     ap.add_argument("--cpu-latent", type=int, default=8, help="latent size of the bounded CPU sample")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -264,9 +274,17 @@ def main():
     model.first_stage_model.set_engine(args.engine)
     peaks = _peaks()
 
-    host = make_host_inputs(args.stage, seed=rank, pin=True)
+    frames_mode = args.shard == "frames" and world > 1
+    shard = (rank, world) if frames_mode else None
+    host = make_host_inputs(args.stage, seed=0 if frames_mode else rank, pin=True)
+    if frames_mode:
+        if T_FRAMES % world:
+            raise SystemExit(f"--shard frames needs 16 % world == 0, got {world}")
+        host = {k: v.pin_memory() for k, v in shard_frames(host, rank, world).items()}
+        config["parallelism"] = f"frames sharded over {world} GPUs ({T_FRAMES // world} per GPU), NCCL all-gather/halo/all-reduce"
     dev_t = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    out_host = torch.empty(T_FRAMES, 3, wl["h"] * 8, wl["h"] * 8, dtype=torch.float16).pin_memory()
+    n_local = T_FRAMES // world if frames_mode else T_FRAMES
+    out_host = torch.empty(n_local, 3, wl["h"] * 8, wl["h"] * 8, dtype=torch.float16).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
 
@@ -290,11 +308,11 @@ def main():
         return float(ms.item()), _native.launch_count() - l0
 
     def step_resident():
-        run_video(model, args.stage, dev_t)
+        run_video(model, args.stage, dev_t, shard)
 
     def step_e2e():
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        frames = run_video(model, args.stage, d)
+        frames = run_video(model, args.stage, d, shard)
         out_host.copy_(frames, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -310,7 +328,7 @@ def main():
 
     breakdown = roof = None
     unet_ms = None
-    if rank == 0 and not args.no_breakdown:
+    if rank == 0 and not args.no_breakdown and not frames_mode:
         breakdown, roof, unet_ms = kernel_breakdown(model, args.stage, dev_t, peaks)
     cpu_b = None
     if rank == 0 and world == 1 and not os.environ.get("HI3D_SKIP_CPU_BASELINE"):
@@ -321,11 +339,12 @@ def main():
                  "sample": f"1 timed Euler step after 1 warm-up (full-width VideoUNet, fp32 oracle port) at {lat}x{lat} latents = {t:.2f} s/step, "
                            f"projected to {wl['h']}x{wl['h']} by UNet FLOP ratio {ratio:.1f} x 25 steps"}
     if rank == 0:
-        fps = T_FRAMES * args.steps * world / (ms / 1e3)
-        fps_e2e = T_FRAMES * args.steps * world / (ms_e2e / 1e3)
+        videos = 1 if frames_mode else world
+        fps = T_FRAMES * args.steps * videos / (ms / 1e3)
+        fps_e2e = T_FRAMES * args.steps * videos / (ms_e2e / 1e3)
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "fp16", "data": "synthetic", "config": config, "engine": args.engine,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if frames_mode else "weak",
+                "vs_baseline": None, "dtype": "fp16", "data": "synthetic", "config": config, "engine": args.engine,
                 "unet_ms_per_sampler_step": unet_ms, "clocks": clk,
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu_b}
