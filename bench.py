@@ -141,7 +141,19 @@ def kernel_breakdown(model, stage: int, dev_t, peaks):
         d = cls.setdefault(k, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
         d["ms"] += ms; d["launches"] += 1; d["flops"] += fl; d["bytes"] += by
     tot = sum(d["ms"] for d in cls.values())
+    # per GEMM shape (rows mode, M, N, K, activation): where the implicit-GEMM time goes
+    shapes = {}
+    for s, e0, e1 in recs:
+        if isinstance(s, ops.Gemm):
+            pp = s.p
+            key = f"mode{pp.mode} M={pp.M} N={pp.N} K={pp.K} act={pp.act}" + (" up" if pp.out_up else "") + \
+                  (" s2" if pp.stride == 2 else "")
+            d = shapes.setdefault(key, dict(ms=0.0, launches=0, flops=0.0))
+            d["ms"] += e0.elapsed_time(e1); d["launches"] += 1; d["flops"] += s.flops
+    top = sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:14]
     out = {}
+    out["gemm_shapes_top"] = {k: dict(ms=round(d["ms"], 3), launches=d["launches"], tflops=round(d["flops"] / d["ms"] / 1e9, 1))
+                              for k, d in top}
     for k, d in cls.items():
         out[k] = dict(ms=round(d["ms"], 3), share=round(d["ms"] / tot, 4), launches=d["launches"])
         if d["flops"]:

@@ -47,7 +47,7 @@ struct T5Params {
   int nseg;
   int M, N, K, mode;
   int BN, stages, n_tiles, total_tiles;
-  int dbg;   // HI3D_TC5_DBG bit mask for bottleneck experiments: 1 skip stores, 2 skip residual/blend/rowbias loads, 4 skip TMEM loads, 8 skip MMA
+  int dbg;   // HI3D_TC5_DBG bit mask for bottleneck experiments: 1 skip stores, 2 skip residual/blend/rowbias loads, 4 skip TMEM loads, 8 skip MMA, 16 skip A loads, 32 skip B loads
   // tile -> rows
   int tw, th, tn;      // CONV2D patch (PLAIN: tw = 128, th = tn = 1; TEMPORAL: tw = ts, th = tf)
   int Wo, Ho, Nimg;    // CONV2D: output W, H, images.  TEMPORAL: Wo = HW, Ho = T, Nimg = B
@@ -130,13 +130,19 @@ HI3D_DEVINL long long t5_map(const T5Params& p, long long m) {
   return ((long long)n * 2 * p.Ho + 2 * y + p.out_py) * (2 * p.Wo) + 2 * x + p.out_px;
 }
 
+// NCTA = 2: the two CTAs of a cluster own the two 128-row halves of a 256-row tile and half of the B tile each;
+// CTA 0 issues tcgen05.mma.cta_group::2 for the pair (operands are read from both CTAs' shared memory, so every B
+// byte is fetched from L2 once per PAIR), each CTA runs the epilogue of its own 128 accumulator rows.
+template <int NCTA>
 __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ T5Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
   const int BN = p.BN, STAGES = p.stages;
-  const uint32_t stage_bytes = T5_A_BYTES + BN * 128;
+  const uint32_t stage_bytes = T5_A_BYTES + (BN / NCTA) * 128;   // per CTA
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / NCTA, nunits = gridDim.x / NCTA;  // a unit = one CTA (pair); units walk (pair-)tiles
   const uint32_t bar_base = base + STAGES * stage_bytes;
   const uint32_t bar_full = bar_base;                      // STAGES x 8
   const uint32_t bar_empty = bar_base + 8 * T5_MAX_STAGES;
@@ -148,84 +154,133 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
   float* sbias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64);   // [2][256]
   uint8_t* scratch = smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048;                  // [EPI_WARPS][32 x 80]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role index
   const int KT = p.K / T5_BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, 1);        // the (leader's) expect_tx arrive; a pair counts both CTAs' bytes on CTA 0
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(bar_acc_full + 8 * b, 1);
-      mbar_init(bar_acc_empty + 8 * b, T5_EPI_WARPS);
+      mbar_init(bar_acc_empty + 8 * b, T5_EPI_WARPS * NCTA);   // pair: both CTAs' epilogue warps report to the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
 
   if (warp == 0) {
     // ======================= TMA producer =======================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-        const T5Tile o = t5_origin(p, mt);
-        const int n0 = nt * BN;
-        int si = 0, so = 0;
-        for (int kt = 0; kt < KT; kt++, it++) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+    // The whole warp walks the loop with warp-uniform values and one elected lane issues: addresses stay in uniform
+    // registers.  (A lane-0-only loop made every TMA / MMA operand go through R2UR waterfall code and the two
+    // single-thread issue loops -- ~600 cycles per k-block -- were the slowest part of the kernel.)
+    uint32_t s = 0, ph = 0;
+    const uint32_t lead_full = (NCTA == 2) ? mapa_cluster(bar_full, 0) : bar_full;   // pair: bytes count on CTA 0
+    const uint32_t txb = ((p.dbg & 16) ? 0u : (uint32_t)T5_A_BYTES) + ((p.dbg & 32) ? 0u : (uint32_t)(BN / NCTA) * 128u);
+    for (int tile = unit0; tile < p.total_tiles; tile += nunits) {
+      const int mu = tile / p.n_tiles, nt = tile - mu * p.n_tiles;
+      const int mt = mu * NCTA + (int)rank;
+      const T5Tile o = t5_origin(p, mt);
+      const int n0 = nt * BN + (int)rank * (BN / NCTA);     // pair: this CTA stages its half of the B rows
+      int si = 0, so = 0;
+      T5Seg sg = p.seg[0];
+      const CUtensorMap* am = &p.amap[sg.map];
+      for (int kt = 0; kt < KT; kt++) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (elect_one()) {
           const uint32_t sA = base + s * stage_bytes;
           const uint32_t sB = sA + T5_A_BYTES;
-          const uint32_t full = bar_full + 8 * s;
-          mbar_expect_tx(full, stage_bytes);
-          const T5Seg sg = p.seg[si];
           const int c = sg.c_off + so;
-          if (p.mode == HI3D_ROWS_PLAIN)
-            tma_load_2d(sA, &p.amap[sg.map], full, c, mt * T5_BM);
-          else if (p.mode == HI3D_ROWS_CONV2D)
-            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
-          else
-            tma_load_4d(sA, &p.amap[sg.map], full, c, o.x0, o.y0 + p.t_off + sg.dt, o.z0);
-          tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
-          so += T5_BK;
-          if (so >= sg.C) { si++; so = 0; }
+          if (NCTA == 2) {
+            // The peer does not arrive on the leader's barrier: its bytes may land before the leader arms the phase (the
+            // tx-count goes negative for a moment), and a release.cluster arrive per k-block serialises the producer.
+            const uint32_t full = lead_full + 8 * s;
+            if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * txb);
+            if (p.dbg & 16) {
+            } else if (p.mode == HI3D_ROWS_PLAIN)
+              tma_load_2d_cg2(sA, am, full, c, mt * T5_BM);
+            else if (p.mode == HI3D_ROWS_CONV2D)
+              tma_load_4d_cg2(sA, am, full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
+            else
+              tma_load_4d_cg2(sA, am, full, c, o.x0, o.y0 + p.t_off + sg.dt, o.z0);
+            if (!(p.dbg & 32)) tma_load_2d_cg2(sB, &p.bmap, full, kt * T5_BK, n0);
+          } else {
+            const uint32_t full = bar_full + 8 * s;
+            mbar_expect_tx(full, txb);
+            if (p.dbg & 16) {
+            } else if (p.mode == HI3D_ROWS_PLAIN)
+              tma_load_2d(sA, am, full, c, mt * T5_BM);
+            else if (p.mode == HI3D_ROWS_CONV2D)
+              tma_load_4d(sA, am, full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
+            else
+              tma_load_4d(sA, am, full, c, o.x0, o.y0 + p.t_off + sg.dt, o.z0);
+            if (!(p.dbg & 32)) tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
+          }
         }
+        __syncwarp();
+        so += T5_BK;
+        if (so >= sg.C && kt + 1 < KT) { si++; so = 0; sg = p.seg[si]; am = &p.amap[sg.map]; }
+        if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    if (NCTA == 2) {
+      // drain: every multicast commit aimed at this CTA's empty barriers has landed before the CTA may exit
+      for (int j = 0; j < STAGES; j++) {
+        // slot s is the oldest outstanding one; a slot never filled keeps its initial phase and passes at once
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      // instruction descriptor: D = f32, A = B = f16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(T5_BM >> 4) << 24);
-      uint32_t it = 0, at = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, at++) {
+    // ======================= MMA issuer (pair: leader CTA only) =======================
+    if (rank == 0) {
+      // instruction descriptor: D = f32, A = B = f16, both K-major, N = BN, M = 128 (per CTA; 256 for the pair)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((T5_BM * NCTA) >> 4) << 24);
+      const uint64_t ad0 = umma_desc_sw128(base), bd0 = umma_desc_sw128(base + T5_A_BYTES);
+      const uint32_t stage16 = stage_bytes >> 4;             // descriptor address field is in 16-byte units
+      uint32_t s = 0, ph = 0, at = 0;
+      for (int tile = unit0; tile < p.total_tiles; tile += nunits, at++) {
         const uint32_t buf = at & 1;
         mbar_wait(bar_acc_empty + 8 * buf, ((at >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * 256;
-        for (int kt = 0; kt < KT; kt++, it++) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int kt = 0; kt < KT; kt++) {
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sA = base + s * stage_bytes;
-          const uint64_t ad = umma_desc_sw128(sA), bd = umma_desc_sw128(sA + T5_A_BYTES);
+          if (elect_one()) {
+            const uint64_t ad = ad0 + (uint64_t)(s * stage16), bd = bd0 + (uint64_t)(s * stage16);
+            if (!(p.dbg & 8)) {
 #pragma unroll
-          for (int k = 0; k < T5_BK / 16; k++)   // +32 bytes along K inside the 128-byte swizzle atom
-            if (!(p.dbg & 8)) tc_mma_f16(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
-          tc_commit(bar_empty + 8 * s);          // frees the smem slot when these MMAs retire
+              for (int k = 0; k < T5_BK / 16; k++) {   // +32 bytes along K inside the 128-byte swizzle atom
+                if (NCTA == 2) tc_mma_f16_cg2(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
+                else tc_mma_f16(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
+              }
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if (NCTA == 2) tc_commit_cg2(bar_empty + 8 * s, 3); else tc_commit(bar_empty + 8 * s);
+          }
+          __syncwarp();
+          if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(bar_acc_full + 8 * buf);       // accumulator complete
+        // accumulator complete
+        if (elect_one()) {
+          if (NCTA == 2) tc_commit_cg2(bar_acc_full + 8 * buf, 3); else tc_commit(bar_acc_full + 8 * buf);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -242,8 +297,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
     uint8_t* scr = scratch + ew * T5_SCR_BYTES;  // 32 rows x 80 bytes (64 data + 16 pad)
     const int crow = lane >> 2, cchk = lane & 3; // coalesced pattern: rows crow + 8 i, 16-byte chunk cchk
     uint32_t at = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, at++) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    const uint32_t lead_acc_empty = (NCTA == 2) ? mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;
+    for (int tile = unit0; tile < p.total_tiles; tile += nunits, at++) {
+      const int mu = tile / p.n_tiles, nt = tile - mu * p.n_tiles;
+      const int mt = mu * NCTA + (int)rank;
       const T5Tile o = t5_origin(p, mt);
       const int n0 = nt * BN;
       const long long m = t5_row(p, mt, o, rl);
@@ -369,14 +426,17 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       // this warp is done reading the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(lead_acc_empty + 8 * buf); else mbar_arrive(bar_acc_empty + 8 * buf);
+      }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -490,24 +550,34 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (g_sm_count <= 0) g_sm_count = 148;
   }
+  // CTA pairs (cta_group::2, 256-row tiles) halve the B bytes each SM pulls from L2 -- the conv / linear main loops are
+  // L2 -> SM bandwidth bound, not tensor bound -- but leave half as many schedulable units: used when there is enough
+  // work to fill the pairs (HI3D_TC5_PAIR=0|1 forces it for experiments).
+  static int pair_env = -2;
+  if (pair_env == -2) { const char* e = getenv("HI3D_TC5_PAIR"); pair_env = e ? atoi(e) : -1; }
+  int ncta = 1;
+  // measured (profiles/r01_microbench_pair.txt): pairs win 5-15 % once the main loop dominates (K >= ~2000: 3x3 convs,
+  // wide temporal convs, ff2 at C >= 640) and lose on short-K, epilogue-bound GEMMs (both epilogues gate one accumulator).
+  if (pair_env == 1 || (pair_env < 0 && p->K >= 1920 && (long long)m_tiles * ((p->N + 255) / 256) >= 2LL * g_sm_count)) ncta = 2;
+  const int m_units = (m_tiles + ncta - 1) / ncta, units = g_sm_count / ncta;
   int BN = 256;
   {
     long long best = -1;
     for (int cand = 256; cand >= 32; cand -= 32) {
       if (p->act == HI3D_ACT_GEGLU && (cand % 64)) continue;     // keep GEGLU output chunks 32-byte aligned
       const long long ntl = (p->N + cand - 1) / cand;
-      const long long rounds = ((long long)m_tiles * ntl + g_sm_count - 1) / g_sm_count;
+      const long long rounds = ((long long)m_units * ntl + units - 1) / units;
       const long long cost = rounds * (cand + 48);
       if (best < 0 || cost < best) { best = cost; BN = cand; }
     }
   }
-  const int stage_bytes = T5_A_BYTES + BN * 128;
+  const int stage_bytes = T5_A_BYTES + (BN / ncta) * 128;
   int stages = T5_SMEM_BUDGET / stage_bytes;
   if (stages > T5_MAX_STAGES) stages = T5_MAX_STAGES;
   if (stages < 2) { return hi3d_gemm(p, stream); }
   tp.BN = BN; tp.stages = stages;
   tp.n_tiles = (p->N + BN - 1) / BN;
-  tp.total_tiles = m_tiles * tp.n_tiles;
+  tp.total_tiles = m_units * tp.n_tiles;      // (pair-)tiles
 
   for (int j = 0; j < nmaps; j++) {
     const cuuint64_t ld = (cuuint64_t)lds[j];
@@ -534,7 +604,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   {
     cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)p->N};
     cuuint64_t str[1] = {(cuuint64_t)p->K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t box[2] = {64, (cuuint32_t)(BN / ncta)};
     if (encode_map(&tp.bmap, p->W, 2, dims, str, box, nullptr)) return -1;
   }
   tp.bias = p->bias; tp.rowbias = (const __half*)p->rowbias; tp.rb_div = p->rb_div; tp.rb_mod = p->rb_mod;
@@ -546,16 +616,26 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   static bool attr_done = false;
   const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
     if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
     attr_done = true;
   }
-  const int grid = tp.total_tiles < g_sm_count ? tp.total_tiles : g_sm_count;
   const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
-  gemm_tc5_kernel<<<grid, T5_THREADS, smem, st>>>(tp);
+  if (ncta == 2) {
+    const int grid = 2 * (tp.total_tiles < units ? tp.total_tiles : units);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T5_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<2>, tp);
+    if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: pair launch: %s", cudaGetErrorString(e)); return -1; }
+  } else {
+    const int grid = tp.total_tiles < g_sm_count ? tp.total_tiles : g_sm_count;
+    gemm_tc5_kernel<1><<<grid, T5_THREADS, smem, st>>>(tp);
+  }
   return check_launch("hi3d_gemm_tc5");
 }

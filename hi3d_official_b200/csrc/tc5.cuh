@@ -17,9 +17,15 @@ HI3D_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 HI3D_DEVINL void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp (the same one every time: commits track the MMAs of the issuing thread)
+HI3D_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 HI3D_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  unsigned long long spins = 0;
+  uint32_t spins = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -28,7 +34,7 @@ HI3D_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1ull << 27)) __trap();  // watchdog: a lost TMA / MMA completion must not hang the GPU
+    if (!done && ++spins > (1u << 27)) __trap();  // watchdog: a lost TMA / MMA completion must not hang the GPU
   }
 }
 HI3D_DEVINL void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -118,6 +124,54 @@ HI3D_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
       : "memory");
 }
 HI3D_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster form one 256-row MMA -----------------------------
+HI3D_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+HI3D_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+HI3D_DEVINL uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+HI3D_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads issued by either CTA of the pair; the completion bytes are counted on the barrier `bar_cluster` (a
+// shared::cluster address, normally the leader CTA's full barrier), the data lands in the issuing CTA's smem.
+HI3D_DEVINL void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+HI3D_DEVINL void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+HI3D_DEVINL void tc_mma_f16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all prior MMAs of the pair retire) on the barrier at the same offset in every CTA of `mask`
+HI3D_DEVINL void tc_commit_cg2(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
 
 // host: encode a tiled fp16 tensor map with SWIZZLE_128B (defined in gemm_tc5.cu)
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
