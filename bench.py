@@ -178,7 +178,9 @@ def cpu_baseline_sample(stage: int, latent: int, steps: int, warmup: int):
     import torch
     from hi3d_official_b200 import configs, spec
     from oracle import hi3d_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    # bounded thread count: on the 128-core GPU host the 8x8-latent sample is all tiny ops and 128 OpenMP threads made one
+    # step take minutes (oversubscription); 16 threads is what the reported `cores` says
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     kw = configs.UNET_STAGE1 if stage == 1 else configs.UNET_STAGE2
     cfg = spec.UNetConfig.from_kwargs(**kw)
     sd = spec.synth_state_dict(spec.unet_param_shapes(cfg), seed=1)
@@ -259,7 +261,7 @@ def main():
         t = cpu_baseline_sample(args.stage, lat, args.steps, args.warmup)
         ratio = unet_step_flops(args.stage, wl["h"]) / unet_step_flops(args.stage, lat)
         fps = T_FRAMES / (NUM_STEPS * t * ratio)
-        cores = os.cpu_count() or 1
+        cores = min(os.cpu_count() or 1, 16)     # threads cpu_baseline_sample() actually uses
         sample = (f"{args.steps} timed Euler steps (CFG-batched full-width VideoUNet fwd, fp32, oracle port) at {lat}x{lat} "
                   f"latents = {t:.2f} s/step; projected to {wl['h']}x{wl['h']} latents by the UNet FLOP ratio {ratio:.1f} "
                   f"x 25 steps (VAE decode not included)")
@@ -347,7 +349,7 @@ def main():
         lat = args.cpu_latent
         t = cpu_baseline_sample(args.stage, lat, 1, 1)
         ratio = unet_step_flops(args.stage, wl["h"]) / unet_step_flops(args.stage, lat)
-        cpu_b = {"value": T_FRAMES / (NUM_STEPS * t * ratio), "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+        cpu_b = {"value": T_FRAMES / (NUM_STEPS * t * ratio), "unit": "frames/s", "cores": min(os.cpu_count() or 1, 16), "kind": "port",
                  "sample": f"1 timed Euler step after 1 warm-up (full-width VideoUNet, fp32 oracle port) at {lat}x{lat} latents = {t:.2f} s/step, "
                            f"projected to {wl['h']}x{wl['h']} by UNet FLOP ratio {ratio:.1f} x 25 steps"}
     if rank == 0:
