@@ -71,8 +71,21 @@ HI3D_DEVINL float warp_max(float v) {
   return v;
 }
 
+// Eight fp16 values = one 16-byte access.  __half2 has user-provided copy operations, so a plain struct of four of them is
+// copied member by member and nvcc emits four 32-bit loads / stores per access (every epilogue, GroupNorm and LayerNorm
+// store in round 1 went out as 4-byte writes: partial sectors, ~30 % of HBM bandwidth).  The copy operations below move
+// the uint4 view instead, which compiles to LDG.128 / STG.128 / LDS.128 / STS.128.
 struct alignas(16) Half8 {
-  __half2 h[4];
+  union {
+    uint4 u;
+    __half2 h[4];
+  };
+  __host__ __device__ Half8() {}
+  __host__ __device__ Half8(const Half8& o) : u(o.u) {}
+  __host__ __device__ Half8& operator=(const Half8& o) {
+    u = o.u;
+    return *this;
+  }
 };
 
 }  // namespace hi3d

@@ -400,9 +400,12 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           }
           __syncwarp();
           const float al = p.alpha, be = 1.f - p.alpha;
+          Half8 w8s[4];                          // distinct registers: a reused one serialises on the previous store
+#pragma unroll
+          for (int i = 0; i < 4; i++) w8s[i] = *reinterpret_cast<const Half8*>(scr + (crow + 8 * i) * 80 + cchk * 16);
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            Half8 w8 = *reinterpret_cast<const Half8*>(scr + (crow + 8 * i) * 80 + cchk * 16);
+            Half8& w8 = w8s[i];
             if (mrow[i] < 0 || !colok) continue;
             if (p.residual != nullptr && !(p.dbg & 2)) {
 #pragma unroll
