@@ -2,11 +2,15 @@
 //
 // One CTA = 128 queries of one (image, head).  Per 128-key tile:
 //   S = Q K^T        tcgen05.mma, A = Q (smem, K-major), B = K tile (smem, K-major)      -> TMEM S[b]  (128 fp32 cols)
-//   softmax          4 warps, one thread per query row: two passes over its TMEM row (max, then exp2 / sum),
-//                    P written back as packed fp16 into the first 64 columns of the same S[b] region
-//   O_j = P V        tcgen05.mma, A = P (TMEM), B = V tile (smem, MN-major: rows = keys)    -> TMEM O[b]   (64 fp32 cols)
-//   O   = O * corr_j + O_j   in the row-owner's registers (fp32), so the accumulator never needs an in-TMEM rescale
-// 256 TMEM columns per CTA (S/P: 128, two O buffers: 2 x 64) and ~114 KB of shared memory, so TWO CTAs share an SM:
+//   softmax          4 warps, one thread per query row.  The kernel is bound by TMEM READ bandwidth (S is 64 KB per
+//                    tile), so S is normally read ONCE: P = exp2(S c - m_ref c) against the running maximum of the
+//                    previous tiles while the tile's own maximum is tracked in the same pass; only when some row of the
+//                    warp grew by more than 2^8 (or on the first tile) the warp falls back to max-then-exp (two reads)
+//                    and rescales.  P goes to its own 64 columns (packed fp16) so that S survives for the fallback.
+//   O  += P V        tcgen05.mma, A = P (TMEM), B = V tile (smem, MN-major: rows = keys), accumulating in TMEM O (64 fp32
+//                    cols).  Because the reference maximum only moves in the fallback path, O needs no per-tile
+//                    correction: it is rescaled in TMEM (ld, multiply, st by the row owner) only there.
+// 256 TMEM columns per CTA (S 128, P 64, O 64) and ~114 KB of shared memory, so TWO CTAs share an SM:
 // while one CTA's softmax warps work on a tile the other CTA's MMAs run, which keeps both the MUFU/FMA pipes and the
 // tensor pipe busy without splitting the softmax state across warpgroups.
 // Warp roles (192 threads): warp 0 = TMA producer (Q once, K/V ring), warp 1 = TMEM allocator + MMA issuer,
@@ -52,9 +56,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
   const uint32_t bar_kv_empty = bar_kv_full + 8 * FA_STAGES;  // [STAGES]
   const uint32_t bar_s_full = bar_kv_empty + 8 * FA_STAGES;   // S written by the MMA (phase flips every tile)
   const uint32_t bar_p_full = bar_s_full + 16;                // P written by the softmax warps
-  const uint32_t bar_o_full = bar_p_full + 16;                // [2]  O[b] written by the MMA
-  const uint32_t bar_o_empty = bar_o_full + 16;               // [2]  O[b] consumed by the softmax warps
-  const uint32_t tmem_slot = bar_o_empty + 16;
+  const uint32_t bar_o_full = bar_p_full + 16;                // O written by the MMA (phase flips every tile)
+  const uint32_t tmem_slot = bar_o_full + 32;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -68,10 +71,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
     for (int s = 0; s < FA_STAGES; s++) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
     mbar_init(bar_s_full, 1);
     mbar_init(bar_p_full, 4);
-    for (int b = 0; b < 2; b++) {
-      mbar_init(bar_o_full + 8 * b, 1);
-      mbar_init(bar_o_empty + 8 * b, 4);
-    }
+    mbar_init(bar_o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 1) {
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
-  // TMEM columns: S / P = [0,128), O[0] = [128,192), O[1] = [192,256)
-  const uint32_t tS0 = tmem_base, tO0 = tmem_base + 128;
+  // TMEM columns: S = [0,128), P = [128,192) (packed fp16), O = [192,256)
+  const uint32_t tS0 = tmem_base, tP0 = tmem_base + 128, tO0 = tmem_base + 192;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -106,23 +106,21 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
       const uint64_t qd = umma_desc_sw128(sQ);
       mbar_wait(bar_q, 0);
       for (int j = 0; j < nkv; j++) {
-        const int b = j & 1, s = j % FA_STAGES;
+        const int s = j % FA_STAGES;
         mbar_wait(bar_kv_full + 8 * s, (j / FA_STAGES) & 1);
         tc_fence_after();
-        // S = Q K^T.  The S/P columns are free: P V of tile j-1 was issued before and tcgen05.mma executes in order.
+        // S = Q K^T.  The S columns are free: the softmax warps signalled P(j-1) after their last read of S(j-1).
         const uint64_t kd = umma_desc_sw128(sKV + s * 2 * FA_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; k++) tc_mma_f16(tS0, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
         tc_commit(bar_s_full);
         mbar_wait(bar_p_full, j & 1);                           // P of tile j is in TMEM
-        mbar_wait(bar_o_empty + 8 * b, ((j >> 1) & 1) ^ 1);    // O[b] of tile j-2 has been consumed
         tc_fence_after();
         const uint64_t vd = umma_desc_sw128_mn(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES);
-        const uint32_t tO = tO0 + b * 64;
 #pragma unroll
         for (int k = 0; k < 8; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
-          tc_mma_f16_ts(tO, tS0 + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, k ? 1u : 0u);
-        tc_commit(bar_o_full + 8 * b);
+          tc_mma_f16_ts(tO0, tP0 + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, (j | k) ? 1u : 0u);
+        tc_commit(bar_o_full);
         tc_commit(bar_kv_empty + 8 * s);
       }
     }
@@ -132,95 +130,120 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
     const int r = q * 32 + lane;                 // query row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale_log2;
-    float oacc[64];
-#pragma unroll
-    for (int i = 0; i < 64; i++) oacc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkv; j++) {
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
-      const uint32_t tS = tS0 + lane_off;
-      // pass 1: row max
-      // (two 32-column TMEM reads in flight, 8 independent max chains: the reduction is latency-, not issue-bound)
-      float mxa[8];
+      const uint32_t tS = tS0 + lane_off, tP = tP0 + lane_off;
+      bool full = (j == 0);
+      if (!full) {
+        // ---- optimistic single read of S: exponentials against the running maximum, tile maximum on the side ----
+        const float moff = m_run * c;
+        float rsa[4] = {0.f, 0.f, 0.f, 0.f};
+        float mxa[4] = {m_run, m_run, m_run, m_run};
+        uint32_t va[32], vb[32];
+        tmem_ld32(tS, va);
 #pragma unroll
-      for (int i = 0; i < 8; i++) mxa[i] = m_run;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; cc += 2) {
-        uint32_t v0[32], v1[32];
-        tmem_ld32(tS + 32 * cc, v0);
-        tmem_ld32(tS + 32 * cc + 32, v1);
-        tmem_ld_wait(v0);
+        for (int cc = 0; cc < 4; cc++) {
+          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+          tmem_ld_wait(cur);
+          if (cc + 1 < 4) tmem_ld32(tS + 32 * (cc + 1), nxt);
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v0[i]));
-        tmem_ld_wait(v1);
-#pragma unroll
-        for (int i = 0; i < 32; i++) mxa[4 + (i & 3)] = fmaxf(mxa[4 + (i & 3)], __uint_as_float(v1[i]));
-      }
-      const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-      const float corr = exp2f((m_run - mx) * c);       // m_run = -inf on the first tile -> 0
-      const float moff = mx * c;
-      m_run = mx;
-      // pass 2: P = exp2(S*c - m*c), row sum (4 independent chains), packed fp16 back into the same TMEM region;
-      // the TMEM read of chunk cc+1 is issued before chunk cc is processed
-      float rsa[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t va[32], vb[32];
-      tmem_ld32(tS, va);
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++) {
-        uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-        uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
-        tmem_ld_wait(cur);
-        if (cc + 1 < 4) tmem_ld32(tS + 32 * (cc + 1), nxt);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i]), c, -moff));
-          const float p1 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i + 1]), c, -moff));
-          rsa[(i >> 1) & 3] += p0 + p1;
-          pk[i >> 1] = pack_half2(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
+            mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(s0, s1));
+            const float p0 = ex2_approx_ftz(fmaf(s0, c, -moff));
+            const float p1 = ex2_approx_ftz(fmaf(s1, c, -moff));
+            rsa[(i >> 1) & 3] += p0 + p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st16(tP + 16 * cc, pk);
         }
-        tmem_st16(tS + 16 * cc, pk);
+        const float tmax = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        // P <= 2^8 keeps fp16 exact enough and far from overflow; a larger jump redoes the tile with the true maximum
+        full = __any_sync(0xffffffffu, (tmax - m_run) * c > 8.0f);
+        if (!full) l_run += (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
+      }
+      if (full) {
+        // ---- max, then exponentials: two reads of S (first tile, or the maximum moved a lot) ----
+        // (two 32-column TMEM reads in flight, 8 independent max chains: the reduction is latency-, not issue-bound)
+        tmem_st_wait();
+        float mxa[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) mxa[i] = m_run;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; cc += 2) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tS + 32 * cc, v0);
+          tmem_ld32(tS + 32 * cc + 32, v1);
+          tmem_ld_wait(v0);
+#pragma unroll
+          for (int i = 0; i < 32; i++) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v0[i]));
+          tmem_ld_wait(v1);
+#pragma unroll
+          for (int i = 0; i < 32; i++) mxa[4 + (i & 3)] = fmaxf(mxa[4 + (i & 3)], __uint_as_float(v1[i]));
+        }
+        const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                               fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+        const float corr = exp2f((m_run - mx) * c);       // m_run = -inf on the first tile -> 0
+        const float moff = mx * c;
+        m_run = mx;
+        if (j > 0) {
+          // the reference moved: bring the accumulator (complete up to tile j-1) to the new one, in place
+          mbar_wait(bar_o_full, (j - 1) & 1);
+          tc_fence_after();
+          const uint32_t tO = tO0 + lane_off;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; cc++) {
+            uint32_t v[16];
+            tmem_ld16(tO + 16 * cc, v);
+            tmem_ld_wait16(v);
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+            tmem_st16(tO + 16 * cc, v);
+          }
+          tmem_st_wait();
+        }
+        float rsa[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t va[32], vb[32];
+        tmem_ld32(tS, va);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+          tmem_ld_wait(cur);
+          if (cc + 1 < 4) tmem_ld32(tS + 32 * (cc + 1), nxt);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i]), c, -moff));
+            const float p1 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i + 1]), c, -moff));
+            rsa[(i >> 1) & 3] += p0 + p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st16(tP + 16 * cc, pk);
+        }
+        l_run = l_run * corr + (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
       }
       tmem_st_wait();
-      const float rs = (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
-      l_run = l_run * corr + rs;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
-      // fold in the previous tile's P V while the tensor core works on this one
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(bar_o_full + 8 * pb, ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        const uint32_t tO = tO0 + pb * 64 + lane_off;
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          uint32_t v[32];
-          tmem_ld32(tO + 32 * cc, v);
-          tmem_ld_wait(v);
-#pragma unroll
-          for (int i = 0; i < 32; i++) oacc[32 * cc + i] = fmaf(oacc[32 * cc + i], corr_prev, __uint_as_float(v[i]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_o_empty + 8 * pb);
-      }
-      corr_prev = corr;
     }
+    float oacc[64];
     {
-      const int pb = (nkv - 1) & 1;
-      mbar_wait(bar_o_full + 8 * pb, ((nkv - 1) >> 1) & 1);
+      mbar_wait(bar_o_full, (nkv - 1) & 1);
       tc_fence_after();
-      const uint32_t tO = tO0 + pb * 64 + lane_off;
+      const uint32_t tO = tO0 + lane_off;
 #pragma unroll
       for (int cc = 0; cc < 2; cc++) {
         uint32_t v[32];
         tmem_ld32(tO + 32 * cc, v);
         tmem_ld_wait(v);
 #pragma unroll
-        for (int i = 0; i < 32; i++) oacc[32 * cc + i] = fmaf(oacc[32 * cc + i], corr_prev, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i++) oacc[32 * cc + i] = __uint_as_float(v[i]);
       }
     }
     const float inv = 1.f / l_run;
