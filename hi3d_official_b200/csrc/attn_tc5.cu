@@ -13,8 +13,12 @@
 // 256 TMEM columns per CTA (S 128, P 64, O 64) and ~114 KB of shared memory, so TWO CTAs share an SM:
 // while one CTA's softmax warps work on a tile the other CTA's MMAs run, which keeps both the MUFU/FMA pipes and the
 // tensor pipe busy without splitting the softmax state across warpgroups.
-// Warp roles (192 threads): warp 0 = TMA producer (Q once, K/V ring), warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = softmax / accumulate / store.
+// Warp roles (320 threads): warp 0 = TMA producer (Q once, K/V ring), warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = softmax: TWO warps per TMEM lane quarter, each owning 64 of the 128 key columns of its rows (the softmax
+// code is a latency-bound dependent chain per row -- profiled at ~0.2 IPC per warp with the softmax warps idle 40 % of the
+// time waiting for S -- so the rows are split across more warps rather than given more registers).  The two warps of a
+// quarter agree once per tile (a 64-thread named barrier) on whether the reference maximum has to move; the row sum is
+// kept per half and added at the end.
 #include <cuda.h>
 #include <string.h>
 
@@ -26,9 +30,10 @@ namespace hi3d {
 constexpr int FA_BM = 128;           // queries per CTA
 constexpr int FA_BN = 128;           // keys per tile
 constexpr int FA_STAGES = 2;         // K/V ring depth per CTA (two CTAs per SM -> 4 tiles in flight per SM)
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 320;
 constexpr int FA_TILE_BYTES = 128 * 128;                 // 128 rows x 64 fp16
-constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256 + 1024;
+constexpr int FA_XCH_BYTES = 4096;                       // per-quarter exchange: votes, partial maxima, partial sums
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 256 + FA_XCH_BYTES + 1024;
 
 HI3D_DEVINL float ex2_approx_ftz(float x) {
   float r;
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
     mbar_init(bar_q, 1);
     for (int s = 0; s < FA_STAGES; s++) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
     mbar_init(bar_s_full, 1);
-    mbar_init(bar_p_full, 4);
+    mbar_init(bar_p_full, 8);
     mbar_init(bar_o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -125,16 +130,23 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
       }
     }
   } else {
-    // ======================= softmax / accumulate warps =======================
-    const int q = warp & 3;
+    // ======================= softmax warps =======================
+    const int q = warp & 3;                      // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;              // which half of the key columns of a tile this warp owns
     const int r = q * 32 + lane;                 // query row within the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const float c = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
+    // exchange area of this quarter: votes[2 tiles][2 halves], partial max / sum [2 tiles][2 halves][32 rows]
+    float* xch = reinterpret_cast<float*>(smem + (bar0 - base) + 256) + q * 256;
+    volatile int* votes = reinterpret_cast<volatile int*>(xch);             // [2][2]
+    volatile float* xmax = xch + 8;                                          // [2][2][32]
+    volatile float* xsum = xch + 8 + 128;                                    // [2][32]
+    const uint32_t tS = tS0 + lane_off + 64u * hf, tP = tP0 + lane_off + 32u * hf, tO = tO0 + lane_off + 32u * hf;
+    float m_run = -INFINITY, l_run = 0.f;        // l_run: sum over THIS warp's columns only
     for (int j = 0; j < nkv; j++) {
       mbar_wait(bar_s_full, j & 1);
       tc_fence_after();
-      const uint32_t tS = tS0 + lane_off, tP = tP0 + lane_off;
+      const int par = j & 1;
       bool full = (j == 0);
       if (!full) {
         // ---- optimistic single read of S: exponentials against the running maximum, tile maximum on the side ----
@@ -143,12 +155,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
         float mxa[4] = {m_run, m_run, m_run, m_run};
         uint32_t va[32], vb[32];
         tmem_ld32(tS, va);
+        tmem_ld32(tS + 32, vb);
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+        for (int cc = 0; cc < 2; cc++) {
+          uint32_t (&cur)[32] = cc ? vb : va;
           tmem_ld_wait(cur);
-          if (cc + 1 < 4) tmem_ld32(tS + 32 * (cc + 1), nxt);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -162,41 +173,42 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
           tmem_st16(tP + 16 * cc, pk);
         }
         const float tmax = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-        // P <= 2^8 keeps fp16 exact enough and far from overflow; a larger jump redoes the tile with the true maximum
-        full = __any_sync(0xffffffffu, (tmax - m_run) * c > 8.0f);
+        // P <= 2^8 keeps fp16 exact enough and far from overflow; a larger jump redoes the tile with the true maximum.
+        // Both warps of the quarter must take the same path (they share the reference and the accumulator rows).
+        const int mine = __any_sync(0xffffffffu, (tmax - m_run) * c > 8.0f) ? 1 : 0;
+        if (lane == 0) votes[par * 2 + hf] = mine;
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + q) : "memory");
+        full = (mine | votes[par * 2 + (hf ^ 1)]) != 0;
         if (!full) l_run += (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
       }
       if (full) {
         // ---- max, then exponentials: two reads of S (first tile, or the maximum moved a lot) ----
-        // (two 32-column TMEM reads in flight, 8 independent max chains: the reduction is latency-, not issue-bound)
         tmem_st_wait();
-        float mxa[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) mxa[i] = m_run;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; cc += 2) {
+        float mxa[4] = {m_run, m_run, m_run, m_run};
+        {
           uint32_t v0[32], v1[32];
-          tmem_ld32(tS + 32 * cc, v0);
-          tmem_ld32(tS + 32 * cc + 32, v1);
+          tmem_ld32(tS, v0);
+          tmem_ld32(tS + 32, v1);
           tmem_ld_wait(v0);
 #pragma unroll
           for (int i = 0; i < 32; i++) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v0[i]));
           tmem_ld_wait(v1);
 #pragma unroll
-          for (int i = 0; i < 32; i++) mxa[4 + (i & 3)] = fmaxf(mxa[4 + (i & 3)], __uint_as_float(v1[i]));
+          for (int i = 0; i < 32; i++) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v1[i]));
         }
-        const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                               fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+        float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+        xmax[(par * 2 + hf) * 32 + lane] = mx;
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + q) : "memory");
+        mx = fmaxf(mx, xmax[(par * 2 + (hf ^ 1)) * 32 + lane]);
         const float corr = exp2f((m_run - mx) * c);       // m_run = -inf on the first tile -> 0
         const float moff = mx * c;
         m_run = mx;
         if (j > 0) {
-          // the reference moved: bring the accumulator (complete up to tile j-1) to the new one, in place
+          // the reference moved: bring this warp's 32 accumulator columns (complete up to tile j-1) to the new one
           mbar_wait(bar_o_full, (j - 1) & 1);
           tc_fence_after();
-          const uint32_t tO = tO0 + lane_off;
 #pragma unroll 1
-          for (int cc = 0; cc < 4; cc++) {
+          for (int cc = 0; cc < 2; cc++) {
             uint32_t v[16];
             tmem_ld16(tO + 16 * cc, v);
             tmem_ld_wait16(v);
@@ -209,12 +221,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
         float rsa[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t va[32], vb[32];
         tmem_ld32(tS, va);
+        tmem_ld32(tS + 32, vb);
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-          uint32_t (&cur)[32] = (cc & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+        for (int cc = 0; cc < 2; cc++) {
+          uint32_t (&cur)[32] = cc ? vb : va;
           tmem_ld_wait(cur);
-          if (cc + 1 < 4) tmem_ld32(tS + 32 * (cc + 1), nxt);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -232,27 +243,22 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
     }
-    float oacc[64];
-    {
-      mbar_wait(bar_o_full, (nkv - 1) & 1);
-      tc_fence_after();
-      const uint32_t tO = tO0 + lane_off;
+    // row sum = both halves
+    xsum[hf * 32 + lane] = l_run;
+    asm volatile("bar.sync %0, 64;\n" ::"r"(1 + q) : "memory");
+    const float inv = 1.f / (l_run + xsum[(hf ^ 1) * 32 + lane]);
+    mbar_wait(bar_o_full, (nkv - 1) & 1);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(tO, v);
+    tmem_ld_wait(v);
+    __half* dst = p.out + (long long)(row0 + q0 + r) * p.C + h * 64 + 32 * hf;
 #pragma unroll
-      for (int cc = 0; cc < 2; cc++) {
-        uint32_t v[32];
-        tmem_ld32(tO + 32 * cc, v);
-        tmem_ld_wait(v);
-#pragma unroll
-        for (int i = 0; i < 32; i++) oacc[32 * cc + i] = __uint_as_float(v[i]);
-      }
-    }
-    const float inv = 1.f / l_run;
-    __half* dst = p.out + (long long)(row0 + q0 + r) * p.C + h * 64;
-#pragma unroll
-    for (int i = 0; i < 64; i += 8) {
+    for (int i = 0; i < 32; i += 8) {
       Half8 o8;
 #pragma unroll
-      for (int k = 0; k < 4; k++) o8.h[k] = __floats2half2_rn(oacc[i + 2 * k] * inv, oacc[i + 2 * k + 1] * inv);
+      for (int k = 0; k < 4; k++)
+        o8.h[k] = __floats2half2_rn(__uint_as_float(v[i + 2 * k]) * inv, __uint_as_float(v[i + 2 * k + 1]) * inv);
       *reinterpret_cast<Half8*>(dst + i) = o8;
     }
   }
