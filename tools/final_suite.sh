@@ -15,5 +15,8 @@ if [ "$T" = all ] || [ "$T" = bench ]; then
 fi
 if [ "$T" = all ] || [ "$T" = ncu ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/fs_launches_s1.csv python tools/one_step.py > gpurun_out/fs_ncu_list.log 2>&1; echo "ncu list rc=$?"
-  timeout 900 ncu --set full --clock-control none -k "regex:gemm_tc5|fmha_tc5|gn_apply|gn_stats|layernorm|tattn" --launch-count 70 -f -o gpurun_out/fs_full_s1 python tools/one_step.py > gpurun_out/fs_ncu_full.log 2>&1; echo "ncu full rc=$?"; ls -la gpurun_out/fs_full_s1.ncu-rep
+  # ~1.6 MB per captured kernel and gpurun_out/ travels back only below 64 MiB: capture to /tmp, copy if small
+  timeout 900 ncu --set full --clock-control none -k "regex:gemm_tc5|fmha_tc5|gn_apply|gn_stats|layernorm|tattn" --launch-skip 8 --launch-count 22 -f -o /tmp/fs_full_s1 python tools/one_step.py > gpurun_out/fs_ncu_full.log 2>&1; echo "ncu full rc=$?"; ls -la /tmp/fs_full_s1.ncu-rep
+  if [ $(stat -c %s /tmp/fs_full_s1.ncu-rep 2>/dev/null || echo 999999999) -lt 45000000 ]; then cp /tmp/fs_full_s1.ncu-rep gpurun_out/; fi
+  ncu -i /tmp/fs_full_s1.ncu-rep --page raw --csv > gpurun_out/fs_full_s1_raw.csv 2>/dev/null; ls -la gpurun_out/fs_full_s1_raw.csv
 fi
