@@ -260,6 +260,15 @@ def main():
                          "frames sharded over the GPUs (strong scaling; K/V all-gather + halo + GN all-reduce per layer)")
     ap.add_argument("--cpu-latent", type=int, default=8, help="latent size of the bounded CPU sample")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: anything a library writes to fd 1 in between (NCCL prints its version
+    # banner there) goes to stderr instead
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(_real_stdout, (json.dumps(line) + "\n").encode())
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -285,7 +294,7 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -376,7 +385,7 @@ def main():
                 "unet_ms_per_sampler_step": unet_ms, "clocks": clk,
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roof, "kernel_breakdown": breakdown, "cpu_baseline": cpu_b}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
