@@ -93,7 +93,11 @@ typedef struct {
 } hi3d_gemm_params;
 
 int hi3d_gemm(const hi3d_gemm_params* p, void* stream);
-/* same contract, tcgen05/TMEM engine (UTCHMMA); selected by the host when validated on the device */
+/* Same contract on the Blackwell-native engine (persistent kernel, TMA operand staging, tcgen05.mma with TMEM
+ * accumulators, CTA pairs on long-K shapes): the production path.  Geometries it does not cover (N < 32, unaligned row
+ * bias, > 4 distinct A sources, ...) are forwarded to hi3d_gemm, with identical results.
+ * Environment (experiments only, read once per process): HI3D_TC5_PAIR=0|1 forces single-CTA / CTA-pair tiles,
+ * HI3D_TC5_DBG=<bit mask> disables parts of the kernel for bottleneck measurements (results are then meaningless). */
 int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream);
 
 /* Tiny channel counts (UNet input 8|17 ch, VAE image 3 ch / latent 4 ch) are zero-padded to 64 channels by
