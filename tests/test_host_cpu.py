@@ -176,3 +176,17 @@ def test_checkpoint_loader_accepts_reference_layouts(tmp_path):
         m2.init_from_ckpt(str(path))
         for k, v in m2.state_dict().items():
             assert torch.equal(v, sd[k]), k
+
+
+def test_flop_count_matches_survey():
+    """tools/count_flops.py (plan-derived) against the reference-graph figures of SURVEY.md §8(d)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sp = importlib.util.spec_from_file_location("count_flops", os.path.join(root, "tools", "count_flops.py"))
+    cf = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(cf)
+    for stage, survey in ((1, 4.061e13), (2, 2.095e14)):
+        per, ref, ours = cf.count(stage)
+        assert abs(ref - survey) / survey < 0.01, (stage, ref, survey)
+        assert 0.90 * ref < ours < ref          # the folds remove a few per cent, nothing else
