@@ -140,6 +140,37 @@ __global__ void gaussian_sample_kernel(const __half* __restrict__ mom, int ld, c
   out[idx] = v * scale;
 }
 
+
+// ---- one-time weight packing (the C-ABI twin of hi3d_official_b200/pack.py) ---------------------------------------
+// src: (Co, Ci, taps) row-major -- nn.Linear [Co, Ci] (taps 1), Conv2d OIHW (taps kh*kw), Conv3d (Co, Ci, 3, 1, 1) (taps 3).
+// dst: fp16 [cout_pad, taps * cin_pad] with K ordered (tap, ci) = the segment order of the implicit-GEMM engine;
+// geglu: destination rows interleave (value_j, gate_j) of the [value ; gate] row blocks (attention.py:87-94).
+HI3D_DEVINL float to_float(float v) { return v; }
+HI3D_DEVINL float to_float(__half v) { return __half2float(v); }
+
+template <typename T>
+__global__ void pack_weight_kernel(const T* __restrict__ w, int Co, int Ci, int taps, int cin_pad, int cout_pad, int geglu,
+                                   __half* __restrict__ out, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int K = taps * cin_pad;
+  const int n = (int)(idx / K), rem = (int)(idx - (long long)n * K);
+  const int t = rem / cin_pad, ci = rem - t * cin_pad;
+  int sn = n;
+  if (geglu) sn = (n & 1) ? (Co >> 1) + (n >> 1) : (n >> 1);
+  float v = 0.f;
+  if (sn < Co && ci < Ci) v = to_float(w[((long long)sn * Ci + ci) * taps + t]);
+  out[idx] = __float2half_rn(v);
+}
+template <typename T>
+__global__ void pack_bias_kernel(const T* __restrict__ b, int n, int n_pad, int geglu, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  int si = i;
+  if (geglu) si = (i & 1) ? (n >> 1) + (i >> 1) : (i >> 1);
+  out[i] = (b != nullptr && si < n) ? to_float(b[si]) : 0.f;
+}
+
 }  // namespace hi3d
 
 using namespace hi3d;
@@ -236,4 +267,35 @@ extern "C" int hi3d_gaussian_sample(const void* moments, int ld, const float* no
                                                                                           noise, C, H * W, scale, out,
                                                                                           total);
   return check_launch("hi3d_gaussian_sample");
+}
+
+extern "C" int hi3d_pack_weight(const void* w, int w_is_fp32, int Co, int Ci, int taps, int cin_pad, int cout_pad,
+                                int geglu_interleave, void* out, void* stream) {
+  if (!w || !out || Co <= 0 || Ci <= 0 || taps <= 0 || cin_pad < Ci || cout_pad < Co || (geglu_interleave && (Co & 1))) {
+    set_error("hi3d_pack_weight: bad arguments (Co=%d Ci=%d taps=%d cin_pad=%d cout_pad=%d)", Co, Ci, taps, cin_pad, cout_pad);
+    return -2;
+  }
+  const long long total = (long long)cout_pad * taps * cin_pad;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (w_is_fp32)
+    pack_weight_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)w, Co, Ci, taps, cin_pad, cout_pad,
+                                                                     geglu_interleave, (__half*)out, total);
+  else
+    pack_weight_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)w, Co, Ci, taps, cin_pad, cout_pad,
+                                                                      geglu_interleave, (__half*)out, total);
+  return check_launch("hi3d_pack_weight");
+}
+
+extern "C" int hi3d_pack_bias(const void* b, int b_is_fp32, int n, int n_pad, int geglu_interleave, float* out,
+                              void* stream) {
+  if (!out || n <= 0 || n_pad < n || (geglu_interleave && (n & 1))) {
+    set_error("hi3d_pack_bias: bad arguments (n=%d n_pad=%d)", n, n_pad);
+    return -2;
+  }
+  const unsigned grid = (unsigned)((n_pad + 255) / 256);
+  if (b_is_fp32)
+    pack_bias_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)b, n, n_pad, geglu_interleave, out);
+  else
+    pack_bias_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)b, n, n_pad, geglu_interleave, out);
+  return check_launch("hi3d_pack_bias");
 }

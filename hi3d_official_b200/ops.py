@@ -255,3 +255,25 @@ def gaussian_sample(moments: torch.Tensor, noise: Optional[torch.Tensor], out: t
         _chk32(noise, "noise")
     N.check(N.load().hi3d_gaussian_sample(moments.data_ptr(), moments.shape[-1], _ptr(noise), n, c, h, w, scale,
                                           out.data_ptr(), _stream()), "hi3d_gaussian_sample")
+
+
+def pack_weight_native(w: torch.Tensor, taps: int, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None,
+                       geglu: bool = False) -> torch.Tensor:
+    """hi3d_pack_weight (the C-ABI twin of pack.py): w = contiguous (Co, Ci, taps...) fp32 / fp16 on the device."""
+    assert w.is_cuda and w.is_contiguous() and w.dtype in (torch.float32, torch.float16)
+    co, ci = w.shape[0], w.shape[1]
+    assert w.numel() == co * ci * taps
+    cip, cop = cin_pad or ci, cout_pad or co
+    out = torch.empty(cop, taps * cip, dtype=torch.float16, device=w.device)
+    N.check(N.load().hi3d_pack_weight(w.data_ptr(), int(w.dtype == torch.float32), co, ci, taps, cip, cop, int(geglu),
+                                      out.data_ptr(), _stream()), "hi3d_pack_weight")
+    return out
+
+
+def pack_bias_native(b: Optional[torch.Tensor], n: int, n_pad: Optional[int] = None, geglu: bool = False,
+                     device=None) -> torch.Tensor:
+    dev = b.device if b is not None else device
+    out = torch.empty(n_pad or n, dtype=torch.float32, device=dev)
+    is32 = int(b is None or b.dtype == torch.float32)
+    N.check(N.load().hi3d_pack_bias(_ptr(b), is32, n, n_pad or n, int(geglu), out.data_ptr(), _stream()), "hi3d_pack_bias")
+    return out

@@ -198,6 +198,16 @@ int hi3d_nhwc_to_nchw(const void* in, int in_ld, int N, int C, int H, int W, flo
 int hi3d_gaussian_sample(const void* moments, int ld, const float* noise, int N, int C, int H, int W, float scale,
                          float* out, void* stream);
 
+/* One-time weight packing (device -> device), the C twin of hi3d_official_b200/pack.py for hosts without torch:
+ * reference layouts as stored in the checkpoints -- nn.Linear [Co, Ci] (taps = 1; attention.py:269-278, 87-113),
+ * Conv2d OIHW (taps = kh*kw; openaimodel.py:107-207, 263-304, model.py:67-151), Conv3d (Co, Ci, 3, 1, 1) (taps = 3;
+ * video_model.py:45-60) -- into the fp16 [cout_pad, taps * cin_pad] K-major matrix of hi3d_gemm (K ordered (tap, ci),
+ * zero padded).  geglu_interleave: rows of the GEGLU projection [value ; gate] are interleaved (value_j, gate_j).
+ * hi3d_pack_bias: fp32 [n_pad] (b may be NULL -> zeros).  Caller owns all buffers. */
+int hi3d_pack_weight(const void* w, int w_is_fp32, int Co, int Ci, int taps, int cin_pad, int cout_pad,
+                     int geglu_interleave, void* out, void* stream);
+int hi3d_pack_bias(const void* b, int b_is_fp32, int n, int n_pad, int geglu_interleave, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

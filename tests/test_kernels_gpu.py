@@ -290,3 +290,23 @@ def test_layout_and_gaussian():
     ref = lat * 0.75 + (init * 3.0 + z) * 0.25
     ops.renoise_blend(lat, init, z, 0.25, 3.0)
     torch.testing.assert_close(lat, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_pack_weight_native_matches_pack_py(dtype):
+    """hi3d_pack_weight / hi3d_pack_bias (C ABI) against the torch packing the plan uses (pack.py), bit for bit."""
+    from hi3d_official_b200 import pack
+    g = torch.Generator(device="cpu").manual_seed(5)
+    w2 = torch.randn(24, 10, 3, 3, generator=g).to(DEV, dtype)
+    assert torch.equal(ops.pack_weight_native(w2.contiguous(), 9, cin_pad=16, cout_pad=32), pack.pack_conv2d(w2, 16, 32))
+    w3 = torch.randn(64, 64, 3, 1, 1, generator=g).to(DEV, dtype)
+    assert torch.equal(ops.pack_weight_native(w3.contiguous(), 3), pack.pack_conv3d_t(w3))
+    wl = torch.randn(40, 72, generator=g).to(DEV, dtype)
+    assert torch.equal(ops.pack_weight_native(wl.contiguous(), 1, cout_pad=64), pack.pack_linear(wl, 64))
+    wg, bg = torch.randn(128, 32, generator=g).to(DEV, dtype), torch.randn(128, generator=g).to(DEV, dtype)
+    pw, pb = pack.pack_geglu(wg, bg)
+    assert torch.equal(ops.pack_weight_native(wg.contiguous(), 1, geglu=True), pw)
+    assert torch.equal(ops.pack_bias_native(bg, 128, geglu=True), pb)
+    b = torch.randn(24, generator=g).to(DEV, dtype)
+    assert torch.equal(ops.pack_bias_native(b, 24, 32), pack.pack_bias(b, 24, 32))
+    assert torch.equal(ops.pack_bias_native(None, 24, 32, device=DEV), pack.pack_bias(None, 24, 32, device=DEV))
