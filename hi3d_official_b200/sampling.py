@@ -412,3 +412,56 @@ class EDMSampler(SingleStepDiffusionSampler):
 
 class EulerEDMSampler(EDMSampler):
     """sampling.py:228-232: EDMSampler whose correction step is the identity (inherited)."""
+
+
+# ------------------------------------------------------------------------------------------------------------
+# SURVEY §8(f) N4: the two other samplers of the sgm surface that Hi3D-style configs can name.  Host-side step
+# algebra only; every denoiser evaluation goes through `self.denoise`, i.e. through the same CUDA launch plan
+# (generic path) -- they take 2x / 1x network evaluations per step and are not fused with the Euler kernels.
+# ------------------------------------------------------------------------------------------------------------
+class HeunEDMSampler(EDMSampler):
+    """sampling.py:236-254.  Second order: the slope at (x, sigma_hat) is averaged with the slope at the Euler point
+    (x_e, sigma_next); the last step (sigma_next = 0) stays first order, which also saves one evaluation."""
+
+    def possible_correction_step(self, euler_step, x, d, dt, next_sigma, denoiser, cond, uc):
+        if float(next_sigma.sum()) < 1e-14:
+            return euler_step
+        sig_n = append_dims(next_sigma, x.ndim)
+        d_next = (euler_step - self.denoise(euler_step, denoiser, next_sigma, cond, uc)) / sig_n
+        heun = x + (d + d_next) / 2.0 * dt
+        return torch.where(sig_n > 0.0, heun, euler_step)
+
+
+class DPMPP2MSampler(BaseDiffusionSampler):
+    """sampling.py:305-379 (DPM-Solver++(2M), Lu et al. 2022) in t = -log(sigma): one evaluation per step; from the
+    second step on the denoised estimate is extrapolated with the previous one (ratio r of the two log-step sizes)."""
+
+    @staticmethod
+    def _t(sigma):                       # sampling_utils.py: to_neg_log_sigma
+        return sigma.log().neg()
+
+    @staticmethod
+    def _sigma(t):                       # sampling_utils.py: to_sigma
+        return t.neg().exp()
+
+    def sampler_step(self, old_denoised, previous_sigma, sigma, next_sigma, denoiser, x, cond, uc=None):
+        denoised = self.denoise(x, denoiser, sigma, cond, uc)
+        t, t_next = self._t(sigma), self._t(next_sigma)
+        h = t_next - t
+        keep = append_dims(self._sigma(t_next) / self._sigma(t), x.ndim)     # sigma_next / sigma
+        gain = append_dims((-h).expm1(), x.ndim)                             # exp(-h) - 1 <= 0
+        x_first = keep * x - gain * denoised
+        if old_denoised is None or float(next_sigma.sum()) < 1e-14:
+            return x_first, denoised
+        r = (t - self._t(previous_sigma)) / h
+        w_new, w_old = append_dims(1 + 1 / (2 * r), x.ndim), append_dims(1 / (2 * r), x.ndim)
+        x_second = keep * x - gain * (w_new * denoised - w_old * old_denoised)
+        return torch.where(append_dims(next_sigma, x.ndim) > 0.0, x_second, x_first), denoised
+
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None, **kwargs):
+        x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
+        prev_d = None
+        for i in self.get_sigma_gen(num_sigmas):
+            x, prev_d = self.sampler_step(prev_d, None if i == 0 else s_in * sigmas[i - 1], s_in * sigmas[i],
+                                          s_in * sigmas[i + 1], denoiser, x, cond, uc=uc)
+        return x

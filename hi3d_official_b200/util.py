@@ -24,6 +24,8 @@ TARGET_ALIASES: Dict[str, str] = {
     "sgm.modules.diffusionmodules.guiders.VanillaCFG": "hi3d_official_b200.sampling.VanillaCFG",
     "sgm.modules.diffusionmodules.guiders.IdentityGuider": "hi3d_official_b200.sampling.IdentityGuider",
     "sgm.modules.diffusionmodules.sampling.EulerEDMSampler": "hi3d_official_b200.sampling.EulerEDMSampler",
+    "sgm.modules.diffusionmodules.sampling.HeunEDMSampler": "hi3d_official_b200.sampling.HeunEDMSampler",
+    "sgm.modules.diffusionmodules.sampling.DPMPP2MSampler": "hi3d_official_b200.sampling.DPMPP2MSampler",
     "sgm.models.autoencoder.AutoencoderKL": "hi3d_official_b200.vae.AutoencoderKL",
     "sgm.models.autoencoder.AutoencoderKLModeOnly": "hi3d_official_b200.vae.AutoencoderKLModeOnly",
     "sgm.modules.diffusionmodules.model.Encoder": "hi3d_official_b200.vae.Encoder",
