@@ -8,10 +8,19 @@ Default workload (N=1): BASELINE.json configs[1], first-stage 16 x 512 x 512 (la
 With --gpus N > 1 (torchrun) every rank runs its own video (BASELINE configs[4] style data parallel, weak scaling,
 no data-path collective); time = max over ranks, value = all videos / that time.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--stage 1|2] [--impl reference]
+`--shard frames` instead shards the 16 frames of ONE video over the ranks (strong scaling, NCCL exchanges in the step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--stage 1|2] [--shard videos|frames] [--impl reference]
+
+stdout carries exactly one line, the JSON (libraries that print to fd 1 are redirected to stderr).  Keys beyond the
+contract: `unet_ms_per_sampler_step` (one eager UNet forward with the host kept ahead of the GPU = the cost of a sampler
+step inside the graph), `kernel_breakdown` (CUDA events around every launch of one instrumented forward: per kernel class
+ms / share / TFLOP/s / GB/s, the top GEMM shapes, and the sum of launches), `roofline` (all GEMM launches of that forward
+against the measured sustained bf16 peak of MEASURED_PEAKS.json).
 
 --impl reference times the oracle port of the reference's CPU path (the reference itself is pure Python and cannot
-travel to the GPU box) on the host cores, on a bounded sample, and prints the same JSON line with impl=reference.
+travel to the GPU box) on the host cores (<= 16 threads: more oversubscribe the small sample), on a bounded sample, and
+prints the same JSON line with impl=reference.
 """
 from __future__ import annotations
 
