@@ -405,3 +405,63 @@ def vae_decode(p: P, z: torch.Tensor, scale_factor: float = 0.18215) -> torch.Te
     """decode_first_stage, diffusion.py:117-135 + AutoencodingEngineLegacy.decode, autoencoder.py:490-505."""
     z = z / scale_factor
     return vae_decoder(p, F.conv2d(z, p["post_quant_conv.weight"], p["post_quant_conv.bias"]))
+
+
+# ----------------------------------------------------------------------------------------------
+# SURVEY §8(f) N1: temporal VAE decoder `VideoDecoder` (time_mode "conv-only", the SVD setting) -- oracle only so far;
+# the CUDA path is the next row to build.  Pinned against the reference class in tests/test_oracle_vs_reference.py.
+# ----------------------------------------------------------------------------------------------
+
+
+def _tpad(w: torch.Tensor):
+    """padding of a Conv3d whose kernel is (kt, kh, kw): k // 2 per axis (temporal_ae.py:88-92, openaimodel.py:263-270)."""
+    return tuple(int(k) // 2 for k in w.shape[2:])
+
+
+def vae_time_stack(p: P, pre: str, x5: torch.Tensor) -> torch.Tensor:
+    """The `time_stack` of temporal_ae.VideoResBlock: openaimodel.ResBlock(dims=3, skip_t_emb=True, no up/down, same
+    channels -> identity skip), openaimodel.py:328-354 with emb_out = 0.  x5: (b, c, t, h, w)."""
+    w1, w2 = p[pre + "in_layers.2.weight"], p[pre + "out_layers.3.weight"]
+    h = F.conv3d(F.silu(_gn(p, pre + "in_layers.0", x5, 1e-5)), w1, p[pre + "in_layers.2.bias"], padding=_tpad(w1))
+    h = F.conv3d(F.silu(_gn(p, pre + "out_layers.0", h, 1e-5)), w2, p[pre + "out_layers.3.bias"], padding=_tpad(w2))
+    return x5 + h
+
+
+def vae_video_resblock(p: P, pre: str, x: torch.Tensor, T: int) -> torch.Tensor:
+    """temporal_ae.VideoResBlock.forward, temporal_ae.py:62-81.  NOTE the blend direction: alpha = sigmoid(mix_factor)
+    weighs the TEMPORAL branch here (x = alpha * time_stack(x) + (1 - alpha) * x), the opposite of the UNet's
+    AlphaBlender."""
+    x = vae_resnet_block(p, pre, x)
+    n, c, hh, ww = x.shape
+    x5 = x.view(n // T, T, c, hh, ww).permute(0, 2, 1, 3, 4)
+    a = torch.sigmoid(p[pre + "mix_factor"]).to(x.dtype)
+    out = a * vae_time_stack(p, pre + "time_stack.", x5) + (1.0 - a) * x5
+    return out.permute(0, 2, 1, 3, 4).reshape(n, c, hh, ww)
+
+
+def vae_video_decoder(p: P, z: torch.Tensor, T: int, pre: str = "decoder.") -> torch.Tensor:
+    """temporal_ae.VideoDecoder (time_mode 'conv-only': VideoResBlocks, plain AttnBlock, AE3DConv only as conv_out)
+    run through Decoder.forward(z, timesteps=T), model.py:715-748 / temporal_ae.py:293-349."""
+    h = F.conv2d(z, p[pre + "conv_in.weight"], p[pre + "conv_in.bias"], padding=1)
+    h = vae_video_resblock(p, pre + "mid.block_1.", h, T)
+    h = vae_attn_block(p, pre + "mid.attn_1.", h)
+    h = vae_video_resblock(p, pre + "mid.block_2.", h, T)
+    nlev = 0
+    while _has(p, f"{pre}up.{nlev}."):
+        nlev += 1
+    for lvl in reversed(range(nlev)):
+        blk = 0
+        while _has(p, f"{pre}up.{lvl}.block.{blk}."):
+            h = vae_video_resblock(p, f"{pre}up.{lvl}.block.{blk}.", h, T)
+            blk += 1
+        if f"{pre}up.{lvl}.upsample.conv.weight" in p:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = F.conv2d(h, p[f"{pre}up.{lvl}.upsample.conv.weight"], p[f"{pre}up.{lvl}.upsample.conv.bias"], padding=1)
+    h = _swish(_gn(p, pre + "norm_out", h, 1e-6))
+    # AE3DConv (temporal_ae.py:84-108): the 2-D conv, then a Conv3d over (t, h, w) of the (b, c, t, h, w) view
+    h = F.conv2d(h, p[pre + "conv_out.weight"], p[pre + "conv_out.bias"], padding=1)
+    n, c, hh, ww = h.shape
+    wt = p[pre + "conv_out.time_mix_conv.weight"]
+    h5 = F.conv3d(h.view(n // T, T, c, hh, ww).permute(0, 2, 1, 3, 4), wt, p[pre + "conv_out.time_mix_conv.bias"],
+                  padding=_tpad(wt))
+    return h5.permute(0, 2, 1, 3, 4).reshape(n, c, hh, ww)

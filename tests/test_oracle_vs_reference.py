@@ -133,3 +133,38 @@ def test_vae_full_size_spec_on_meta():
     mine = {k: v for k, v in spec.vae_param_shapes(spec.VAEConfig.from_ddconfig(R.VAE_DD, 4)).items()
             if not k.startswith(("quant_conv", "post_quant_conv"))}
     assert mine == ref
+
+
+@pytest.mark.parametrize("vks", [[3, 1, 1], 3])
+def test_video_decoder_oracle_matches_reference(vks):
+    """the oracle restatement of temporal_ae.VideoDecoder (time_mode 'conv-only'; kernel (3,1,1) as in
+    SVD and the full 3x3x3 default) against the unmodified reference class, seeded synthetic weights."""
+    R.setup()
+    from sgm.modules.autoencoding.temporal_ae import VideoDecoder
+    torch.manual_seed(0)
+    dd = dict(R.VAE_DD, ch=32, ch_mult=[1, 2, 4, 4], attn_type="vanilla")
+    ref = VideoDecoder(**dd, video_kernel_size=vks, time_mode="conv-only").eval()
+    g = torch.Generator().manual_seed(11)
+    sd = {}
+    for k, v in ref.state_dict().items():
+        if k.endswith("mix_factor"):
+            sd[k] = torch.full_like(v, 0.3)
+        elif v.ndim == 1 and ("norm" in k or "in_layers.0" in k or "out_layers.0" in k) and k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif v.ndim == 1:
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:                       # incl. the zero_module'd out_layers conv of every time_stack (F8)
+            fan_in = v[0].numel()
+            sd[k] = torch.randn(v.shape, generator=g) * fan_in ** -0.5
+    ref.load_state_dict(sd, strict=True)
+    T = 3
+    z = torch.randn(2 * T, 4, 8, 8, generator=g)
+    with torch.no_grad():
+        a = ref(z, timesteps=T)
+        b = O.vae_video_decoder({"decoder." + k: v for k, v in sd.items()}, z, T)
+    assert a.shape == (2 * T, 3, 64, 64)
+    torch.testing.assert_close(b, a, rtol=1e-4, atol=2e-4)
+    # the temporal branch matters: shuffling the frames changes more than a permutation of the output
+    with torch.no_grad():
+        a2 = ref(z.flip(0), timesteps=T).flip(0)
+    assert (a2 - a).abs().max() > 1e-3
