@@ -282,6 +282,50 @@ def vae_param_shapes(cfg: VAEConfig) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
+def video_decoder_param_shapes(cfg: VAEConfig, video_kernel_size=(3, 1, 1)) -> "OrderedDict[str, Tuple[int, ...]]":
+    """temporal_ae.VideoDecoder, time_mode 'conv-only' (temporal_ae.py:18-108, 293-349): the 2-D
+    decoder's keys (prefix `decoder.` kept for symmetry with vae_param_shapes) plus, per ResnetBlock, a `time_stack`
+    ResBlock(dims=3, no emb) and a `mix_factor`, and the `time_mix_conv` of the AE3DConv output conv.  The order is the
+    reference's registration order (mix_factor parameter after time_stack; buffers n/a for 'learned')."""
+    k3 = tuple(video_kernel_size) if not isinstance(video_kernel_size, int) else (video_kernel_size,) * 3
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+
+    def rb(q, ci, co):
+        s[q + "mix_factor"] = (1,)
+        s[q + "norm1.weight"] = (ci,); s[q + "norm1.bias"] = (ci,)
+        s[q + "conv1.weight"] = (co, ci, 3, 3); s[q + "conv1.bias"] = (co,)
+        s[q + "norm2.weight"] = (co,); s[q + "norm2.bias"] = (co,)
+        s[q + "conv2.weight"] = (co, co, 3, 3); s[q + "conv2.bias"] = (co,)
+        if ci != co:
+            s[q + "nin_shortcut.weight"] = (co, ci, 1, 1); s[q + "nin_shortcut.bias"] = (co,)
+        t = q + "time_stack."
+        s[t + "in_layers.0.weight"] = (co,); s[t + "in_layers.0.bias"] = (co,)
+        s[t + "in_layers.2.weight"] = (co, co) + k3; s[t + "in_layers.2.bias"] = (co,)
+        s[t + "out_layers.0.weight"] = (co,); s[t + "out_layers.0.bias"] = (co,)
+        s[t + "out_layers.3.weight"] = (co, co) + k3; s[t + "out_layers.3.bias"] = (co,)
+
+    def attn(q, c):
+        s[q + "norm.weight"] = (c,); s[q + "norm.bias"] = (c,)
+        for n in ("q", "k", "v", "proj_out"):
+            s[q + n + ".weight"] = (c, c, 1, 1); s[q + n + ".bias"] = (c,)
+    nres = len(cfg.ch_mult)
+    bi = cfg.ch * cfg.ch_mult[-1]
+    s["decoder.conv_in.weight"] = (bi, cfg.z_channels, 3, 3); s["decoder.conv_in.bias"] = (bi,)
+    rb("decoder.mid.block_1.", bi, bi); attn("decoder.mid.attn_1.", bi); rb("decoder.mid.block_2.", bi, bi)
+    for lvl in reversed(range(nres)):
+        bo = cfg.ch * cfg.ch_mult[lvl]
+        for b in range(cfg.num_res_blocks + 1):
+            rb(f"decoder.up.{lvl}.block.{b}.", bi, bo)
+            bi = bo
+        if lvl != 0:
+            s[f"decoder.up.{lvl}.upsample.conv.weight"] = (bi, bi, 3, 3); s[f"decoder.up.{lvl}.upsample.conv.bias"] = (bi,)
+    s["decoder.norm_out.weight"] = (bi,); s["decoder.norm_out.bias"] = (bi,)
+    s["decoder.conv_out.weight"] = (cfg.out_ch, bi, 3, 3); s["decoder.conv_out.bias"] = (cfg.out_ch,)
+    s["decoder.conv_out.time_mix_conv.weight"] = (cfg.out_ch, cfg.out_ch) + k3
+    s["decoder.conv_out.time_mix_conv.bias"] = (cfg.out_ch,)
+    return s
+
+
 # ------------------------------------------------------------------------------------------------
 # Seeded synthetic weights
 # ------------------------------------------------------------------------------------------------

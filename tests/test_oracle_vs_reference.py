@@ -168,3 +168,14 @@ def test_video_decoder_oracle_matches_reference(vks):
     with torch.no_grad():
         a2 = ref(z.flip(0), timesteps=T).flip(0)
     assert (a2 - a).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("vks", [[3, 1, 1], 3])
+def test_video_decoder_param_spec_matches_reference_on_meta(vks):
+    R.setup()
+    from sgm.modules.autoencoding.temporal_ae import VideoDecoder
+    with torch.device("meta"):
+        ref = VideoDecoder(**dict(R.VAE_DD, attn_type="vanilla"), video_kernel_size=vks, time_mode="conv-only")
+    ref_shapes = {"decoder." + k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    mine = spec.video_decoder_param_shapes(spec.VAEConfig.from_ddconfig(R.VAE_DD, 4), vks)
+    assert dict(mine) == ref_shapes
