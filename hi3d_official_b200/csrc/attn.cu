@@ -358,12 +358,8 @@ extern "C" int hi3d_attention_d64(const void* qkv, int n_img, int L, int heads, 
     return -2;
   }
   if (heads > 65535 || n_img > 65535) { set_error("hi3d_attention_d64: grid too large"); return -2; }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FMHA_SMEM);
-    if (e != cudaSuccess) { set_error("hi3d_attention_d64: %s", cudaGetErrorString(e)); return -1; }
-    attr_done = true;
-  }
+  static bool attr_done[HI3D_MAX_DEVICES];
+  if (ensure_dyn_smem(fmha_d64_kernel, FMHA_SMEM, attr_done, "hi3d_attention_d64")) return -1;
   dim3 grid((L + FQ - 1) / FQ, heads, n_img);
   fmha_d64_kernel<<<grid, FMHA_THREADS, FMHA_SMEM, (cudaStream_t)stream>>>(
       (const __half*)qkv, L, heads * 64, scale * 1.4426950408889634f, (__half*)out);

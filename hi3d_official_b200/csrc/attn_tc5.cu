@@ -293,12 +293,8 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   fp.L = L; fp.C = C; fp.heads = heads;
   fp.scale_log2 = scale * 1.4426950408889634f;
   fp.out = (__half*)out;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM);
-    if (e != cudaSuccess) { set_error("hi3d_attention_d64_tc5: %s", cudaGetErrorString(e)); return -1; }
-    attr_done = true;
-  }
+  static bool attr_done[HI3D_MAX_DEVICES];
+  if (ensure_dyn_smem(fmha_tc5_kernel, FA_SMEM, attr_done, "hi3d_attention_d64_tc5")) return -1;
   dim3 grid(L / FA_BM, heads, n_img);
   fmha_tc5_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(fp);
   return check_launch("hi3d_attention_d64_tc5");

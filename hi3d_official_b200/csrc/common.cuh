@@ -13,6 +13,21 @@ namespace hi3d {
 // ---- error plumbing (host) -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+// One process may drive several GPUs: one-time per-device state (opt-in shared memory attributes, SM count) is
+// indexed by the CURRENT device, never kept in a single process-wide flag.
+constexpr int HI3D_MAX_DEVICES = 64;
+int current_device();                       // cudaGetDevice(), clamped to [0, HI3D_MAX_DEVICES)
+int device_sm_count();                      // SM count of the current device (cached per device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); `done` = a static bool[HI3D_MAX_DEVICES]
+template <typename K>
+int ensure_dyn_smem(K kernel, int bytes, bool* done, const char* who) {
+  const int d = current_device();
+  if (done[d]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return -1; }
+  done[d] = true;
+  return 0;
+}
 
 // ---- async copy / ldmatrix / mma ---------------------------------------------------------------
 HI3D_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -26,6 +26,21 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= HI3D_MAX_DEVICES) d = 0;
+  return d;
+}
+int device_sm_count() {
+  static int cnt[HI3D_MAX_DEVICES];     // zero-initialised; benign race (idempotent)
+  const int d = current_device();
+  if (cnt[d] <= 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    cnt[d] = v > 0 ? v : 148;
+  }
+  return cnt[d];
+}
 int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
@@ -275,16 +290,9 @@ template <int MODE, int BN>
 static int launch_gemm(const hi3d_gemm_params& p, cudaStream_t st) {
   constexpr int STAGES = 3;
   using SM = GemmSmem<BN, STAGES>;
-  static bool attr_done = false;  // benign race: idempotent
+  static bool attr_done[HI3D_MAX_DEVICES];  // per device; benign race: idempotent
   auto kern = gemm_mma_kernel<MODE, BN, STAGES>;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
-    if (e != cudaSuccess) {
-      set_error("hi3d_gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return -1;
-    }
-    attr_done = true;
-  }
+  if (ensure_dyn_smem(kern, SM::TOTAL, attr_done, "hi3d_gemm")) return -1;
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN);
   kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(p);
   return check_launch("hi3d_gemm");

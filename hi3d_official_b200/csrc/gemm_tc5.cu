@@ -511,11 +511,25 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims
 
 static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-static int g_sm_count = 0;
+// experiment knobs, read from the environment ONCE per process (not per call: getenv on every eager launch was measurable
+// in the un-graphed frame-sharded mode); hi3d_gemm_tc5_set_pair_mode overrides the pair knob for tests
+static int g_pair_mode = -2;      // -2 unread, -1 auto, 0 single CTA, 1 CTA pairs
+static int g_dbg = -1;            // -1 unread
+static void read_env_once() {
+  if (g_pair_mode == -2) { const char* e = getenv("HI3D_TC5_PAIR"); g_pair_mode = e ? atoi(e) : -1; }
+  if (g_dbg < 0) { const char* e = getenv("HI3D_TC5_DBG"); g_dbg = e ? atoi(e) : 0; }
+}
 
 }  // namespace hi3d
 
 using namespace hi3d;
+
+extern "C" int hi3d_gemm_tc5_set_pair_mode(int mode) {
+  if (mode < -1 || mode > 1) { set_error("hi3d_gemm_tc5_set_pair_mode: mode must be -1 (auto), 0 or 1"); return -2; }
+  read_env_once();
+  g_pair_mode = mode;
+  return 0;
+}
 
 extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   int rc = validate_gemm(p, "hi3d_gemm_tc5");
@@ -580,17 +594,12 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   // costs its MMA columns plus a fixed term (A-operand traffic / epilogue set-up); this accounts both for the padding
   // of N and for wave quantisation over the SMs (e.g. N = 1280 with 64 row-tiles: 5 x 256 -> 3 rounds, 8 x 160 -> 4
   // rounds of much shorter tiles).  Ties go to the wider tile.
-  if (g_sm_count <= 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
+  const int g_sm_count = device_sm_count();
+  read_env_once();
   // CTA pairs (cta_group::2, 256-row tiles) halve the B bytes each SM pulls from L2 -- the conv / linear main loops are
   // L2 -> SM bandwidth bound, not tensor bound -- but leave half as many schedulable units: used when there is enough
   // work to fill the pairs (HI3D_TC5_PAIR=0|1 forces it for experiments).
-  static int pair_env = -2;
-  if (pair_env == -2) { const char* e = getenv("HI3D_TC5_PAIR"); pair_env = e ? atoi(e) : -1; }
+  const int pair_env = g_pair_mode;
   int ncta = 1;
   // measured (profiles/r01_microbench_pair.txt): pairs win 5-15 % once the main loop dominates (K >= ~2000: 3x3 convs,
   // wide temporal convs, ff2 at C >= 640) and lose on short-K, epilogue-bound GEMMs (both epilogues gate one accumulator).
@@ -647,16 +656,12 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.rb_ld = p->rb_ld; tp.act = p->act; tp.residual = (const __half*)p->residual; tp.res_ld = p->res_ld;
   tp.blend_x = (const __half*)p->blend_x; tp.blend_ld = p->blend_ld; tp.alpha = p->alpha;
   tp.out = (__half*)p->out; tp.out_ld = p->out_ld;
-  { const char* e = getenv("HI3D_TC5_DBG"); tp.dbg = e ? atoi(e) : 0; }
+  tp.dbg = g_dbg;
 
-  static bool attr_done = false;
+  static bool attr_done1[HI3D_MAX_DEVICES], attr_done2[HI3D_MAX_DEVICES];
   const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
-    if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
-    attr_done = true;
-  }
+  if (ensure_dyn_smem(gemm_tc5_kernel<1>, smem_total, attr_done1, "hi3d_gemm_tc5") ||
+      ensure_dyn_smem(gemm_tc5_kernel<2>, smem_total, attr_done2, "hi3d_gemm_tc5")) return -1;
   const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
   if (ncta == 2) {
     const int grid = 2 * (tp.total_tiles < units ? tp.total_tiles : units);

@@ -159,7 +159,7 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int Co, int Ci, int 
   int sn = n;
   if (geglu) sn = (n & 1) ? (Co >> 1) + (n >> 1) : (n >> 1);
   float v = 0.f;
-  if (sn < Co && ci < Ci) v = to_float(w[((long long)sn * Ci + ci) * taps + t]);
+  if (n < Co && sn < Co && ci < Ci)     // rows >= Co are padding (zeros) also in the interleaved GEGLU order v = to_float(w[((long long)sn * Ci + ci) * taps + t]);
   out[idx] = __float2half_rn(v);
 }
 template <typename T>
@@ -168,7 +168,7 @@ __global__ void pack_bias_kernel(const T* __restrict__ b, int n, int n_pad, int 
   if (i >= n_pad) return;
   int si = i;
   if (geglu) si = (i & 1) ? (n >> 1) + (i >> 1) : (i >> 1);
-  out[i] = (b != nullptr && si < n) ? to_float(b[si]) : 0.f;
+  out[i] = (b != nullptr && i < n && si < n) ? to_float(b[si]) : 0.f;
 }
 
 }  // namespace hi3d

@@ -23,9 +23,16 @@ HI3D_DEVINL bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
   return pred != 0;
 }
+// Deadlock watchdog: a lost TMA / MMA completion must not hang the GPU (and the box lease) forever.  It is WALL-CLOCK
+// based (%globaltimer, checked every 4096 failed polls): a single wait that lasts 4 s is a protocol bug, while a
+// pre-empted, time-sliced or profiler-serialised run -- which could exhaust any fixed spin count -- never comes close.
+// -DHI3D_NO_WATCHDOG compiles it out.
 HI3D_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#ifndef HI3D_NO_WATCHDOG
   uint32_t spins = 0;
+  uint64_t t0 = 0;
+#endif
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -34,7 +41,14 @@ HI3D_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();  // watchdog: a lost TMA / MMA completion must not hang the GPU
+#ifndef HI3D_NO_WATCHDOG
+    if (!done && (++spins & 4095u) == 0u) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+#endif
   }
 }
 HI3D_DEVINL void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

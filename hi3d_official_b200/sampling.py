@@ -200,6 +200,9 @@ class FusedDenoiser:
         self.shard = None if shard is None or shard[1] == 1 else (int(shard[0]), int(shard[1]))
 
     def __call__(self, input, sigma, c):
+        if self.shard is not None:
+            raise NotImplementedError("a frame-sharded FusedDenoiser can only be evaluated by the fused Euler step "
+                                      "(the generic closure has no cross-rank exchanges)")
         return self.denoiser(self.network, input, sigma, c, **self.kwargs)
 
     def fusable(self) -> bool:
@@ -385,6 +388,13 @@ class EDMSampler(SingleStepDiffusionSampler):
             st = self._fused_state(denoiser, x, cond, default(uc, cond), _refresh)
             if st is not None and type(self).possible_correction_step is EDMSampler.possible_correction_step:
                 return st.step(x, sigma, next_sigma)
+        if isinstance(denoiser, FusedDenoiser) and denoiser.shard is not None:
+            # the generic path below would run VideoUNet.forward on this rank's frames as if they were a whole clip (no
+            # K/V, halo or GroupNorm exchange): silently wrong results or diverging ranks
+            raise NotImplementedError(
+                "frame-sharded sampling is only implemented on the fused Euler path (EulerEDMSampler + "
+                "LinearPredictionGuider + VScalingWithEDMcNoise, s_churn = 0, fp32 CUDA latents); got "
+                f"{type(self).__name__} / {type(self.guider).__name__}, gamma={gamma}, x {x.dtype} on {x.device}")
         sigma_hat = sigma * (gamma + 1.0)
         if gamma > 0:
             eps = torch.randn_like(x) * self.s_noise

@@ -99,6 +99,10 @@ class VideoUNet(nn.Module):
         self._packed: Optional[dict] = None
         self._plans: Dict[tuple, "_Plan"] = {}
         self.engine = os.environ.get("HI3D_ENGINE", "tc5")     # "tc5" = tcgen05/TMEM/TMA engine, "mma" = mma.sync engine
+        # packed weights, launch plans and captured graphs derive from the parameters: ANY load that reaches this module
+        # -- its own load_state_dict or a parent's (DiffusionEngine.init_from_ckpt recurses through
+        # _load_from_state_dict and never calls the override below) -- must drop them
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self._invalidate())
 
     # ---- parameter lifecycle ---------------------------------------------------------------------------
     def _invalidate(self):

@@ -225,14 +225,20 @@ class AutoencoderKL(nn.Module):
         self._plans: Dict[tuple, _VAEPlan] = {}
         self.engine = os.environ.get("HI3D_ENGINE", "tc5")     # "tc5" = tcgen05/TMEM/TMA engine, "mma" = mma.sync engine
         self.max_batch_size = ignored.get("max_batch_size", None)
+        # a parent's load_state_dict (DiffusionEngine.init_from_ckpt) recurses through _load_from_state_dict and never
+        # reaches the override below: invalidate the packed weights / plans from a pre-hook as well
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self._invalidate())
 
     # -- lifecycle ----------------------------------------------------------------------------------------------------
-    def _apply(self, fn, *a, **k):
+    def _invalidate(self):
         self._packed, self._plans = None, {}
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed, self._plans = None, {}
+        self._invalidate()
         return super().load_state_dict(*a, **k)
 
     def set_engine(self, engine: str):

@@ -99,6 +99,10 @@ int hi3d_gemm(const hi3d_gemm_params* p, void* stream);
  * Environment (experiments only, read once per process): HI3D_TC5_PAIR=0|1 forces single-CTA / CTA-pair tiles,
  * HI3D_TC5_DBG=<bit mask> disables parts of the kernel for bottleneck measurements (results are then meaningless). */
 int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream);
+/* Test hook: -1 = automatic choice between single-CTA and CTA-pair (cta_group::2, 256-row) tiles (default, or the value of
+ * HI3D_TC5_PAIR at first use), 0 = always single CTA, 1 = always CTA pairs.  Process-wide; the parity tests run every
+ * geometry under both settings (no reference counterpart: the reference's cuDNN / cuBLAS pick their own tiles). */
+int hi3d_gemm_tc5_set_pair_mode(int mode);
 
 /* Tiny channel counts (UNet input 8|17 ch, VAE image 3 ch / latent 4 ch) are zero-padded to 64 channels by
  * hi3d_sampler_pre / hi3d_nchw_to_nhwc so that the same engine serves input_blocks.0.0 (video_model.py:186-191),

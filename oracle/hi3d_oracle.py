@@ -109,8 +109,15 @@ def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
     q = q.view(b, n, heads, d).transpose(1, 2)
     k = k.view(b, k.shape[1], heads, d).transpose(1, 2)
     v = v.view(b, v.shape[1], heads, d).transpose(1, 2)
-    s = torch.matmul(q, k.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.matmul(torch.softmax(s.float(), dim=-1).to(q.dtype), v)
+    # same arithmetic for every batch element; batch chunks only bound the size of the materialised score matrix
+    # (32 x 5 x 16384^2 fp32 scores of the stage-2 top level would be 172 GB)
+    per = heads * n * k.shape[2] * 4
+    step = max(1, min(b, (2 << 30) // max(per, 1)))
+    outs = []
+    for i in range(0, b, step):
+        s = torch.matmul(q[i:i + step], k[i:i + step].transpose(-1, -2)) * (d ** -0.5)
+        outs.append(torch.matmul(torch.softmax(s.float(), dim=-1).to(q.dtype), v[i:i + step]))
+    o = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
     return o.transpose(1, 2).reshape(b, n, hd)
 
 

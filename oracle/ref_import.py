@@ -3,7 +3,9 @@
 `oracle/hi3d_oracle.py` can be validated against it and (b) golden fixtures under
 `tests/golden/` can be generated (see `tools/make_golden.py`).
 
-The reference cannot travel to the GPU box, so nothing on a `-m gpu` path imports this.
+On the GPU box /root/reference does not exist; there the byte-for-byte copy of the needed modules staged by
+`oracle/build_ref.py` under `oracle/_ref/` (git-ignored, travels with the snapshot) is used instead -- only by
+`bench.py`'s reference arm / cpu_baseline, never by the product and never by a `-m gpu` parity test.
 Stubs follow SURVEY.md App. D: pytorch_lightning / omegaconf / kornia / open_clip are only
 needed at module-import time of files we never execute.
 """
@@ -13,7 +15,14 @@ import types
 
 import torch.nn as nn
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REF_ROOT = os.environ.get("HI3D_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "sgm")) and os.path.isdir(os.path.join(_STAGED, "sgm")):
+    REF_ROOT = _STAGED
+
+
+def is_staged_copy() -> bool:
+    return REF_ROOT == _STAGED
 
 
 def available() -> bool:

@@ -310,3 +310,17 @@ def test_pack_weight_native_matches_pack_py(dtype):
     b = torch.randn(24, generator=g).to(DEV, dtype)
     assert torch.equal(ops.pack_bias_native(b, 24, 32), pack.pack_bias(b, 24, 32))
     assert torch.equal(ops.pack_bias_native(None, 24, 32, device=DEV), pack.pack_bias(None, 24, 32, device=DEV))
+
+
+def test_pack_geglu_padded_rows_are_zero():
+    """with cout_pad / n_pad > Co the interleaved GEGLU order must zero-fill the padding rows (they used to be
+    filled with copies of real value / gate rows because the interleave was applied before the range check)."""
+    from hi3d_official_b200 import pack
+    g = torch.Generator(device="cpu").manual_seed(6)
+    wg, bg = torch.randn(128, 32, generator=g).to(DEV), torch.randn(128, generator=g).to(DEV)
+    pw, pb = pack.pack_geglu(wg, bg)
+    got_w = ops.pack_weight_native(wg.contiguous(), 1, cin_pad=64, cout_pad=192, geglu=True)
+    got_b = ops.pack_bias_native(bg, 128, 192, geglu=True)
+    assert got_w.shape == (192, 64) and got_b.shape == (192,)
+    assert torch.equal(got_w[:128, :32], pw) and not bool(got_w[128:].any()) and not bool(got_w[:, 32:].any())
+    assert torch.equal(got_b[:128], pb) and not bool(got_b[128:].any())
