@@ -19,7 +19,22 @@
 // time waiting for S -- so the rows are split across more warps rather than given more registers).  The two warps of a
 // quarter agree once per tile (a 64-thread named barrier) on whether the reference maximum has to move; the row sum is
 // kept per half and added at the end.
+//
+// Round-2 changes (profiles/r01_ncu_fmha_notes.txt: the softmax warps sat 24 % of their samples in the bar_s_full spin,
+// MUFU 52 % busy, tensor pipe 30 %):
+//   * S(j+1) = Q K(j+1)^T is issued BEFORE P(j) V(j): the S columns are dead once all softmax warps have signalled P(j),
+//     so the next tile's scores are computed while P V of this tile still waits its turn on the tensor pipe and the
+//     softmax warps start tile j+1 one MMA (~256 cycles) earlier.  P is single-buffered, so a warp waits for bar_o_full
+//     of tile j (P V(j) retired) before its FIRST tmem store of P(j+1) -- after it has loaded S and computed the first
+//     chunk of exponentials.
+//   * TMA producer / MMA issuer loops are whole-warp loops with elect.sync around the issue (uniform registers; the
+//     lane-0-only form cost 30 % in the GEMM, DESIGN.md lesson 1).
+//   * packed-fp32 softmax arithmetic (FFMA2 / FADD2): 6 issue slots per pair of scores instead of 9.
+//   * EMU > 0: a fraction (EMU / 4) of the exponentials is computed on the FMA pipe (Cody-Waite range reduction +
+//     cubic minimax polynomial, max relative error 7.5e-5, far below the fp16 rounding of P) to take load off the MUFU
+//     pipe, which bounds the kernel at 16384 ex2 per tile = 1024 cycles per tile-step and SM (FlashAttention-4's trick).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -41,6 +56,40 @@ HI3D_DEVINL float ex2_approx_ftz(float x) {
   return r;
 }
 
+// 2^x for a pair on the FMA pipe: n = round(x) through the 1.5 * 2^23 magic constant (the integer lands in the low mantissa
+// bits of t), f = x - n in [-0.5, 0.5], cubic minimax p(f) ~ 2^f (max relative error 7.5e-5), result = p * 2^n by adding
+// n << 23 to the exponent field.  x is clamped at -126 (2^-126 ~ 0 for a softmax weight); x <= 8 by the lazy-maximum rule.
+HI3D_DEVINL float2 ex2_emulated2(float2 x) {
+  const float MAGIC = 12582912.0f;
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 t = __fadd2_rn(x, make_float2(MAGIC, MAGIC));
+  const float2 n = __fadd2_rn(t, make_float2(-MAGIC, -MAGIC));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.0551716648f, 0.0551716648f), f, make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// P = 2^(s c - moff) for 32 scores of one row -> 16 packed half2; row sum into two packed-fp32 accumulators.
+template <int EMU>
+HI3D_DEVINL void softmax_exp32(const uint32_t (&cur)[32], float c, float nmoff, uint32_t (&pk)[16], float2 (&rs)[2]) {
+  const float2 c2 = make_float2(c, c), m2 = make_float2(nmoff, nmoff);
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float2 x = __ffma2_rn(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), c2, m2);
+    float2 pe;
+    if (((i >> 1) & 3) < EMU) pe = ex2_emulated2(x);
+    else pe = make_float2(ex2_approx_ftz(x.x), ex2_approx_ftz(x.y));
+    rs[(i >> 1) & 1] = __fadd2_rn(rs[(i >> 1) & 1], pe);
+    pk[i >> 1] = pack_half2(pe.x, pe.y);
+  }
+}
+
 struct FaParams {
   CUtensorMap qkv_map;     // 2-D view of the packed [rows, 3C] matrix, box {64, 128}
   int L, C, heads;
@@ -48,6 +97,7 @@ struct FaParams {
   __half* out;
 };
 
+template <int EMU>
 __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -91,36 +141,55 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
   const uint32_t tS0 = tmem_base, tP0 = tmem_base + 128, tO0 = tmem_base + 192;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ======================= TMA producer: whole warp walks the loop, one elected lane issues =======================
+    if (elect_one()) {
       mbar_expect_tx(bar_q, FA_TILE_BYTES);
       tma_load_2d(sQ, &p.qkv_map, bar_q, h * 64, row0 + q0);
-      for (int j = 0; j < nkv; j++) {
-        const int s = j % FA_STAGES;
-        mbar_wait(bar_kv_empty + 8 * s, ((j / FA_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; j++) {
+      const int s = j % FA_STAGES;
+      mbar_wait(bar_kv_empty + 8 * s, ((j / FA_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         const uint32_t full = bar_kv_full + 8 * s;
         mbar_expect_tx(full, 2 * FA_TILE_BYTES);
         tma_load_2d(sKV + s * 2 * FA_TILE_BYTES, &p.qkv_map, full, p.C + h * 64, row0 + j * FA_BN);
         tma_load_2d(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES, &p.qkv_map, full, 2 * p.C + h * 64, row0 + j * FA_BN);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // S = Q K^T : M 128, N 128, A/B K-major.   O = P V : M 128, N 64, A from TMEM, B MN-major (bit 16).
-      const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
-      const uint64_t qd = umma_desc_sw128(sQ);
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < nkv; j++) {
-        const int s = j % FA_STAGES;
-        mbar_wait(bar_kv_full + 8 * s, (j / FA_STAGES) & 1);
-        tc_fence_after();
-        // S = Q K^T.  The S columns are free: the softmax warps signalled P(j-1) after their last read of S(j-1).
-        const uint64_t kd = umma_desc_sw128(sKV + s * 2 * FA_TILE_BYTES);
+    // ======================= MMA issuer =======================
+    // S = Q K^T : M 128, N 128, A/B K-major.   O = P V : M 128, N 64, A from TMEM, B MN-major (bit 16).
+    const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(FA_BN >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+    const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+    const uint64_t qd = umma_desc_sw128(sQ);
+    mbar_wait(bar_q, 0);
+    // prologue: S(0)
+    mbar_wait(bar_kv_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint64_t kd = umma_desc_sw128(sKV);
 #pragma unroll
-        for (int k = 0; k < 4; k++) tc_mma_f16(tS0, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
-        tc_commit(bar_s_full);
-        mbar_wait(bar_p_full, j & 1);                           // P of tile j is in TMEM
-        tc_fence_after();
+      for (int k = 0; k < 4; k++) tc_mma_f16(tS0, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
+      tc_commit(bar_s_full);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; j++) {
+      const int s = j % FA_STAGES;
+      mbar_wait(bar_p_full, j & 1);                           // P(j) is in TMEM; every softmax warp is done with S(j)
+      if (j + 1 < nkv) {
+        const int s1 = (j + 1) % FA_STAGES;
+        mbar_wait(bar_kv_full + 8 * s1, ((j + 1) / FA_STAGES) & 1);
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        if (j + 1 < nkv) {                                    // S(j+1) first: the softmax warps start on it while P V(j) runs
+          const uint64_t kd = umma_desc_sw128(sKV + ((j + 1) % FA_STAGES) * 2 * FA_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; k++) tc_mma_f16(tS0, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
+          tc_commit(bar_s_full);
+        }
         const uint64_t vd = umma_desc_sw128_mn(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
@@ -128,6 +197,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
         tc_commit(bar_o_full);
         tc_commit(bar_kv_empty + 8 * s);
       }
+      __syncwarp();
     }
   } else {
     // ======================= softmax warps =======================
@@ -150,8 +220,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
       bool full = (j == 0);
       if (!full) {
         // ---- optimistic single read of S: exponentials against the running maximum, tile maximum on the side ----
-        const float moff = m_run * c;
-        float rsa[4] = {0.f, 0.f, 0.f, 0.f};
+        const float nmoff = -(m_run * c);
+        float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         float mxa[4] = {m_run, m_run, m_run, m_run};
         uint32_t va[32], vb[32];
         tmem_ld32(tS, va);
@@ -160,15 +230,14 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
         for (int cc = 0; cc < 2; cc++) {
           uint32_t (&cur)[32] = cc ? vb : va;
           tmem_ld_wait(cur);
-          uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
-            mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(s0, s1));
-            const float p0 = ex2_approx_ftz(fmaf(s0, c, -moff));
-            const float p1 = ex2_approx_ftz(fmaf(s1, c, -moff));
-            rsa[(i >> 1) & 3] += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
+          for (int i = 0; i < 32; i += 2)
+            mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
+          uint32_t pk[16];
+          softmax_exp32<EMU>(cur, c, nmoff, pk, rs);
+          if (cc == 0) {                 // P is single-buffered: P V of the previous tile must have retired
+            mbar_wait(bar_o_full, (j - 1) & 1);
+            tc_fence_after();
           }
           tmem_st16(tP + 16 * cc, pk);
         }
@@ -179,7 +248,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
         if (lane == 0) votes[par * 2 + hf] = mine;
         asm volatile("bar.sync %0, 64;\n" ::"r"(1 + q) : "memory");
         full = (mine | votes[par * 2 + (hf ^ 1)]) != 0;
-        if (!full) l_run += (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
+        if (!full) l_run += (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
       }
       if (full) {
         // ---- max, then exponentials: two reads of S (first tile, or the maximum moved a lot) ----
@@ -218,7 +287,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
           }
           tmem_st_wait();
         }
-        float rsa[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         uint32_t va[32], vb[32];
         tmem_ld32(tS, va);
         tmem_ld32(tS + 32, vb);
@@ -227,16 +296,10 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
           uint32_t (&cur)[32] = cc ? vb : va;
           tmem_ld_wait(cur);
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i]), c, -moff));
-            const float p1 = ex2_approx_ftz(fmaf(__uint_as_float(cur[i + 1]), c, -moff));
-            rsa[(i >> 1) & 3] += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
-          }
+          softmax_exp32<EMU>(cur, c, -moff, pk, rs);
           tmem_st16(tP + 16 * cc, pk);
         }
-        l_run = l_run * corr + (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
+        l_run = l_run * corr + (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -274,6 +337,24 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
 
 using namespace hi3d;
 
+// fraction of the exponentials computed on the FMA pipe: EMU / 4 (0, 1 or 2); -1 = unread (HI3D_FMHA_EMU, else default)
+static int g_fmha_emu = -1;
+constexpr int FA_EMU_DEFAULT = 0;
+
+extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
+  if (quarters < 0 || quarters > 2) { set_error("hi3d_attention_tc5_set_exp_emulation: 0, 1 or 2 (quarters of the exponentials)"); return -2; }
+  g_fmha_emu = quarters;
+  return 0;
+}
+
+template <int EMU>
+static int launch_fmha(const FaParams& fp, dim3 grid, cudaStream_t st) {
+  static bool attr_done[HI3D_MAX_DEVICES];
+  if (ensure_dyn_smem(fmha_tc5_kernel<EMU>, FA_SMEM, attr_done, "hi3d_attention_d64_tc5")) return -1;
+  fmha_tc5_kernel<EMU><<<grid, FA_THREADS, FA_SMEM, st>>>(fp);
+  return check_launch("hi3d_attention_d64_tc5");
+}
+
 extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream) {
   if (!qkv || !out || n_img <= 0 || L <= 0 || heads <= 0 || ((uintptr_t)qkv & 15) || ((uintptr_t)out & 15)) {
     set_error("hi3d_attention_d64_tc5: bad arguments (n_img=%d L=%d heads=%d)", n_img, L, heads);
@@ -293,9 +374,15 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   fp.L = L; fp.C = C; fp.heads = heads;
   fp.scale_log2 = scale * 1.4426950408889634f;
   fp.out = (__half*)out;
-  static bool attr_done[HI3D_MAX_DEVICES];
-  if (ensure_dyn_smem(fmha_tc5_kernel, FA_SMEM, attr_done, "hi3d_attention_d64_tc5")) return -1;
+  if (g_fmha_emu < 0) {
+    const char* e = getenv("HI3D_FMHA_EMU");
+    g_fmha_emu = e ? atoi(e) : FA_EMU_DEFAULT;
+    if (g_fmha_emu < 0 || g_fmha_emu > 2) g_fmha_emu = FA_EMU_DEFAULT;
+  }
   dim3 grid(L / FA_BM, heads, n_img);
-  fmha_tc5_kernel<<<grid, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(fp);
-  return check_launch("hi3d_attention_d64_tc5");
+  switch (g_fmha_emu) {
+    case 1: return launch_fmha<1>(fp, grid, (cudaStream_t)stream);
+    case 2: return launch_fmha<2>(fp, grid, (cudaStream_t)stream);
+    default: return launch_fmha<0>(fp, grid, (cudaStream_t)stream);
+  }
 }

@@ -159,7 +159,8 @@ __global__ void pack_weight_kernel(const T* __restrict__ w, int Co, int Ci, int 
   int sn = n;
   if (geglu) sn = (n & 1) ? (Co >> 1) + (n >> 1) : (n >> 1);
   float v = 0.f;
-  if (n < Co && sn < Co && ci < Ci)     // rows >= Co are padding (zeros) also in the interleaved GEGLU order v = to_float(w[((long long)sn * Ci + ci) * taps + t]);
+  // rows >= Co are padding (zeros) also in the interleaved GEGLU order
+  if (n < Co && sn < Co && ci < Ci) v = to_float(w[((long long)sn * Ci + ci) * taps + t]);
   out[idx] = __float2half_rn(v);
 }
 template <typename T>

@@ -148,6 +148,10 @@ int hi3d_attention_d64(const void* qkv, int n_img, int L, int heads, float scale
 /* same contract on tcgen05 / TMEM / TMA (S and P*V accumulators in tensor memory, P fed back from TMEM);
  * sequences that are not a multiple of 128 keys are forwarded to hi3d_attention_d64. */
 int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream);
+/* Tuning / test hook of hi3d_attention_d64_tc5: `quarters` / 4 of the softmax exponentials (0, 1 or 2 quarters) are evaluated
+ * on the FMA pipe (range reduction + cubic polynomial, relative error 7.5e-5 before the fp16 rounding of P) instead of the
+ * MUFU pipe that bounds the kernel.  Process-wide; default from HI3D_FMHA_EMU, else the measured best. */
+int hi3d_attention_tc5_set_exp_emulation(int quarters);
 
 /* Temporal self-attention core over the frame axis (T <= 16), head dim 64, for every (clip, pixel, head):
  * token row of (b, t, s) is (b*T + t)*S + s -- the "(b t) s c -> (b s) t c" rearrange of

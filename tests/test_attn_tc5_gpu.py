@@ -5,8 +5,18 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from hi3d_official_b200 import ops  # noqa: E402
+from hi3d_official_b200 import _native, ops  # noqa: E402
 from test_kernels_gpu import DEV, H, close, rnd  # noqa: E402
+
+
+@pytest.fixture(params=[0, 1, 2], ids=["mufu", "emu25", "emu50"], autouse=True)
+def exp_emulation(request):
+    """Every case runs with 0 / 25 % / 50 % of the softmax exponentials on the FMA pipe (cubic polynomial) -- the
+    production default is one of them (attn_tc5.cu FA_EMU_DEFAULT)."""
+    lib = _native.load()
+    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(request.param), "set_exp_emulation")
+    yield request.param
+    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(0), "set_exp_emulation")
 
 
 def ref_attn(qkv, n_img, L, heads):
@@ -16,7 +26,8 @@ def ref_attn(qkv, n_img, L, heads):
 
 
 @pytest.mark.parametrize("n_img,L,heads,scale", [(1, 128, 1, 1.0), (2, 256, 2, 1.0), (3, 1024, 5, 1.0), (1, 4096, 2, 1.0),
-                                                 (2, 1024, 3, 3.0), (1, 384, 1, 0.3)])
+                                                 (2, 1024, 3, 3.0), (1, 384, 1, 0.3), (1, 512, 1, 1.0), (2, 16384, 1, 1.0),
+                                                 (1, 640, 2, 6.0)])
 def test_attention_tc5(n_img, L, heads, scale):
     C = heads * 64
     qkv = (rnd(n_img * L, 3 * C) * scale).to(H)
