@@ -152,6 +152,10 @@ int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float s
  * on the FMA pipe (range reduction + cubic polynomial, relative error 7.5e-5 before the fp16 rounding of P) instead of the
  * MUFU pipe that bounds the kernel.  Process-wide; default from HI3D_FMHA_EMU, else the measured best. */
 int hi3d_attention_tc5_set_exp_emulation(int quarters);
+/* Kernel variant of hi3d_attention_d64_tc5: 0 = eight softmax warps share one score tile, reference maximum and P barrier
+ * per CTA; 1 = the 128 keys of a tile are two independent 64-key pipelines (own score / P columns, accumulator, barriers and
+ * per-row state), merged once at the end.  Process-wide; default from HI3D_FMHA_VARIANT, else the measured best. */
+int hi3d_attention_tc5_set_variant(int variant);
 
 /* Temporal self-attention core over the frame axis (T <= 16), head dim 64, for every (clip, pixel, head):
  * token row of (b, t, s) is (b*T + t)*S + s -- the "(b t) s c -> (b s) t c" rearrange of

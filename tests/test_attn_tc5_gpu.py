@@ -9,14 +9,19 @@ from hi3d_official_b200 import _native, ops  # noqa: E402
 from test_kernels_gpu import DEV, H, close, rnd  # noqa: E402
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["mufu", "emu25", "emu50"], autouse=True)
-def exp_emulation(request):
-    """Every case runs with 0 / 25 % / 50 % of the softmax exponentials on the FMA pipe (cubic polynomial) -- the
-    production default is one of them (attn_tc5.cu FA_EMU_DEFAULT)."""
+@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2)],
+                ids=["shared-mufu", "shared-emu25", "shared-emu50", "split-mufu", "split-emu25", "split-emu50"], autouse=True)
+def kernel_variant(request):
+    """Every case runs on both kernel variants (shared-row CTA / split half-tile pipelines) with 0 / 25 % / 50 % of the
+    softmax exponentials on the FMA pipe (cubic polynomial) -- the production default is one of the six
+    (attn_tc5.cu FA_VARIANT_DEFAULT, FA_EMU_DEFAULT)."""
     lib = _native.load()
-    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(request.param), "set_exp_emulation")
+    variant, emu = request.param
+    _native.check(lib.hi3d_attention_tc5_set_variant(variant), "set_variant")
+    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(emu), "set_exp_emulation")
     yield request.param
-    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(0), "set_exp_emulation")
+    _native.check(lib.hi3d_attention_tc5_set_variant(0), "set_variant")
+    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(1), "set_exp_emulation")
 
 
 def ref_attn(qkv, n_img, L, heads):
