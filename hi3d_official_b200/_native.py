@@ -57,6 +57,9 @@ _SIGS = {
     "hi3d_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_void_p]),
+    "hi3d_groupnorm_apply_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                            C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hi3d_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "hi3d_attention_d64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
@@ -65,6 +68,14 @@ _SIGS = {
     "hi3d_attention_tc5_set_variant": (C.c_int, [C.c_int]),
     "hi3d_temporal_attention_d64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                               C.c_void_p, C.c_void_p]),
+    "hi3d_temporal_attention_d64_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "hi3d_symm_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "hi3d_symm_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hi3d_symm_close": (C.c_int, [C.c_void_p]),
+    "hi3d_symm_free": (C.c_int, [C.c_void_p]),
+    "hi3d_peer_xchg_bytes": (C.c_int64, [C.c_int]),
+    "hi3d_peer_exchange": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "hi3d_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "hi3d_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hi3d_timestep_embedding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),

@@ -2,6 +2,8 @@
 //   fmha_d64_kernel      spatial self-attention, L = H*W keys per image  (flash-style online softmax)
 //   tattn_d64_kernel     temporal self-attention over T <= 16 frames per (clip, pixel, head)
 // Both read a packed fp16 [rows, 3C] q|k|v matrix produced by one fused QKV GEMM and write fp16 [rows, C].
+#include <string.h>
+
 #include "common.cuh"
 
 namespace hi3d {
@@ -181,18 +183,33 @@ fmha_d64_kernel(const __half* __restrict__ qkv, int L, int C, float scale_log2, 
 // ================================================================================================
 constexpr int TA_WARPS = 4;
 
-__global__ void __launch_bounds__(TA_WARPS * 32)
-tattn_d64_kernel(const __half* __restrict__ qkv, int B, int T, int S, int heads, float scale_log2,
-                 __half* __restrict__ out, long long n_items) {
+// One launch covers the pixel strip [s0, s0 + s_cnt) of every clip for ALL T = Tl * world frames.  Unsharded runs have
+// world = 1 (one buffer, the whole pixel range).  Frame-sharded runs: rank r owns frames [r Tl, (r+1) Tl) of
+// every clip in ITS qkv / out buffers and computes strip r of the pixels -- the q|k|v rows of the other ranks' frames are
+// read straight from their (IPC-mapped) buffers over NVLink and the output rows of their frames are stored straight into
+// their buffers: the "all-gather before temporal attention" never materialises, no rank computes a row twice, and 1/4 of the
+// bytes of a K/V gather cross the links (q|k|v of 1/world of the pixels in, 1/world of the outputs out).
+struct TaParams {
+  const __half* qkv[HI3D_MAX_PEERS];   // [B * Tl * S, 3C] of the rank that owns frames [r Tl, (r+1) Tl)
+  __half* out[HI3D_MAX_PEERS];         // [B * Tl * S, C]
+  int B, Tl, world, S, heads;
+  int s0, s_cnt;
+  float scale_log2;
+  long long n_items;                   // B * s_cnt * heads
+};
+
+__global__ void __launch_bounds__(TA_WARPS * 32) tattn_d64_kernel(const __grid_constant__ TaParams p) {
   __shared__ __align__(1024) uint8_t smem[TA_WARPS * 3 * 2048];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long item = (long long)blockIdx.x * TA_WARPS + warp;
-  if (item >= n_items) return;
+  if (item >= p.n_items) return;
+  const int heads = p.heads, S = p.S, Tl = p.Tl, T = p.Tl * p.world;
+  const float scale_log2 = p.scale_log2;
   const int C = heads * 64;
   const int h = (int)(item % heads);
   const long long bs = item / heads;
-  const int s = (int)(bs % S);
-  const int b = (int)(bs / S);
+  const int s = p.s0 + (int)(bs % p.s_cnt);
+  const int b = (int)(bs / p.s_cnt);
   const int ld = 3 * C;
   const uint32_t sQ = smem_u32(smem) + warp * (3 * 2048);
   const uint32_t sK = sQ + 2048, sV = sQ + 4096;
@@ -203,7 +220,9 @@ tattn_d64_kernel(const __half* __restrict__ qkv, int B, int T, int S, int heads,
   for (int i = 0; i < 4; i++) {
     const int t = (lane >> 3) + 4 * i;
     const bool v = t < T;
-    const __half* row = qkv + ((long long)(b * T + (v ? t : 0)) * S + s) * ld + h * 64 + chunk * 8;
+    const int tt = v ? t : 0;
+    const int owner = tt / Tl, tl = tt - owner * Tl;
+    const __half* row = p.qkv[owner] + ((long long)(b * Tl + tl) * S + s) * ld + h * 64 + chunk * 8;
     cp_async16(sQ + swz128(t, chunk), row, v);
     cp_async16(sK + swz128(t, chunk), row + C, v);
     cp_async16(sV + swz128(t, chunk), row + 2 * C, v);
@@ -276,9 +295,11 @@ tattn_d64_kernel(const __half* __restrict__ qkv, int B, int T, int S, int heads,
     const int t = (lane >> 3) + 4 * i;
     if (t < T) {
       const uint4 v = *reinterpret_cast<const uint4*>(sQg + swz128(t, chunk));
-      *reinterpret_cast<uint4*>(out + ((long long)(b * T + t) * S + s) * C + h * 64 + chunk * 8) = v;
+      const int owner = t / Tl, tl = t - owner * Tl;
+      *reinterpret_cast<uint4*>(p.out[owner] + ((long long)(b * Tl + tl) * S + s) * C + h * 64 + chunk * 8) = v;
     }
   }
+  if (p.world > 1) __threadfence_system();     // peer stores of the output rows are performed before the kernel ends
 }
 
 // ================================================================================================
@@ -366,6 +387,13 @@ extern "C" int hi3d_attention_d64(const void* qkv, int n_img, int L, int heads, 
   return check_launch("hi3d_attention_d64");
 }
 
+static int launch_tattn(const TaParams& tp, cudaStream_t st, const char* who) {
+  const long long blocks = (tp.n_items + TA_WARPS - 1) / TA_WARPS;
+  if (blocks > 2147483647LL) { set_error("%s: too many items", who); return -2; }
+  if (blocks > 0) tattn_d64_kernel<<<(unsigned)blocks, TA_WARPS * 32, 0, st>>>(tp);
+  return check_launch(who);
+}
+
 extern "C" int hi3d_temporal_attention_d64(const void* qkv, int B, int T, int S, int heads, float scale, void* out,
                                            void* stream) {
   if (!qkv || !out || B <= 0 || T <= 0 || T > 16 || S <= 0 || heads <= 0 || ((uintptr_t)qkv & 15) ||
@@ -373,12 +401,40 @@ extern "C" int hi3d_temporal_attention_d64(const void* qkv, int B, int T, int S,
     set_error("hi3d_temporal_attention_d64: bad arguments (B=%d T=%d S=%d heads=%d); T must be <= 16", B, T, S, heads);
     return -2;
   }
-  const long long items = (long long)B * S * heads;
-  const long long blocks = (items + TA_WARPS - 1) / TA_WARPS;
-  if (blocks > 2147483647LL) { set_error("hi3d_temporal_attention_d64: too many items"); return -2; }
-  tattn_d64_kernel<<<(unsigned)blocks, TA_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)qkv, B, T, S, heads, scale * 1.4426950408889634f, (__half*)out, items);
-  return check_launch("hi3d_temporal_attention_d64");
+  TaParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.qkv[0] = (const __half*)qkv; tp.out[0] = (__half*)out;
+  tp.B = B; tp.Tl = T; tp.world = 1; tp.S = S; tp.heads = heads; tp.s0 = 0; tp.s_cnt = S;
+  tp.scale_log2 = scale * 1.4426950408889634f;
+  tp.n_items = (long long)B * S * heads;
+  return launch_tattn(tp, (cudaStream_t)stream, "hi3d_temporal_attention_d64");
+}
+
+extern "C" int hi3d_temporal_attention_d64_sharded(void* const* qkv_of_rank, void* const* out_of_rank, int rank, int world,
+                                                   int B, int T_local, int S, int heads, float scale, void* stream) {
+  if (!qkv_of_rank || !out_of_rank || world < 1 || world > HI3D_MAX_PEERS || rank < 0 || rank >= world || B <= 0 ||
+      T_local <= 0 || T_local * world > 16 || S <= 0 || heads <= 0) {
+    set_error("hi3d_temporal_attention_d64_sharded: bad arguments (rank=%d world=%d B=%d T_local=%d S=%d heads=%d); "
+              "T_local * world must be <= 16", rank, world, B, T_local, S, heads);
+    return -2;
+  }
+  TaParams tp;
+  memset(&tp, 0, sizeof(tp));
+  for (int r = 0; r < world; r++) {
+    if (!qkv_of_rank[r] || !out_of_rank[r] || ((uintptr_t)qkv_of_rank[r] & 15) || ((uintptr_t)out_of_rank[r] & 15)) {
+      set_error("hi3d_temporal_attention_d64_sharded: null / unaligned buffer of rank %d", r);
+      return -2;
+    }
+    tp.qkv[r] = (const __half*)qkv_of_rank[r]; tp.out[r] = (__half*)out_of_rank[r];
+  }
+  const int per = (S + world - 1) / world;             // pixel strip of this rank (the last strips may be short / empty)
+  int s0 = rank * per, s1 = s0 + per;
+  if (s0 > S) s0 = S;
+  if (s1 > S) s1 = S;
+  tp.B = B; tp.Tl = T_local; tp.world = world; tp.S = S; tp.heads = heads; tp.s0 = s0; tp.s_cnt = s1 - s0;
+  tp.scale_log2 = scale * 1.4426950408889634f;
+  tp.n_items = (long long)B * tp.s_cnt * heads;
+  return launch_tattn(tp, (cudaStream_t)stream, "hi3d_temporal_attention_d64_sharded");
 }
 
 extern "C" int hi3d_softmax_rows(void* s, int64_t rows, int L, float scale, void* stream) {

@@ -595,7 +595,7 @@ using namespace hi3d;
 
 // fraction of the exponentials computed on the FMA pipe: EMU / 4 (0, 1 or 2); -1 = unread (HI3D_FMHA_EMU, else default)
 static int g_fmha_emu = -1;
-constexpr int FA_EMU_DEFAULT = 1;     // measured best of {0, 1, 2} at every Hi3D shape (profiles/r02_microbench_attn.txt)
+constexpr int FA_EMU_DEFAULT = 0;     // measured (profiles/r02_microbench_attn.txt): 1/4 helps the shared-row kernel (+2..18 %), hurts the split one
 
 extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
   if (quarters < 0 || quarters > 2) { set_error("hi3d_attention_tc5_set_exp_emulation: 0, 1 or 2 (quarters of the exponentials)"); return -2; }
@@ -604,7 +604,7 @@ extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
 }
 
 static int g_fmha_variant = -1;    // 0 = shared-row kernel, 1 = split half-tile pipelines; -1 = unread (HI3D_FMHA_VARIANT)
-constexpr int FA_VARIANT_DEFAULT = 0;
+constexpr int FA_VARIANT_DEFAULT = 1;  // split pipelines: 783 vs 744 TFLOP/s at L = 16384, 768 vs 726 at L = 4096 x 10 heads
 
 extern "C" int hi3d_attention_tc5_set_variant(int variant) {
   if (variant < 0 || variant > 1) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows) or 1 (split pipelines)"); return -2; }

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
                 long long rows_per_cta, const float* __restrict__ fin, double count, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int apply_silu, __half* __restrict__ y,
-                long long y_sample_rows, long long y_row_off) {
+                long long y_sample_rows, long long y_row_off, __half* __restrict__ y_prev, __half* __restrict__ y_next,
+                long long frame_rows) {
   __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
   const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
   const int tid = threadIdx.x, n = blockIdx.y;
@@ -156,15 +157,29 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
     }
     return v;
   };
+  // Frame-sharded temporal GroupNorm: y is a haloed [n, T_local + 2, frame_rows, C] buffer.  The first local
+  // frame is ALSO stored into the trailing halo slot of the previous rank's buffer and the last local frame into the leading
+  // halo slot of the next rank's (peer stores over NVLink): the one-frame halo exchange of the (3,1,1) conv rides on this
+  // kernel's stores.  y_prev / y_next are the peers' buffer bases (NULL at the clip boundary: that slot stays zero = padding).
+  const long long last0 = rows_per_sample - frame_rows;
+  __half* yp = y_prev ? y_prev + ((long long)n * y_sample_rows + (y_sample_rows - frame_rows)) * C + c0 : nullptr;
+  __half* yn = y_next ? y_next + ((long long)n * y_sample_rows - last0) * C + c0 : nullptr;
+  bool remote = false;
+  auto put = [&](long long rr, const Half8& o) {
+    *reinterpret_cast<Half8*>(yb + rr * C) = o;
+    if (yp != nullptr && rr < frame_rows) { *reinterpret_cast<Half8*>(yp + rr * C) = o; remote = true; }
+    if (yn != nullptr && rr >= last0) { *reinterpret_cast<Half8*>(yn + rr * C) = o; remote = true; }
+  };
   long long r = r0 + rl;
   for (; r + (long long)(GN_UNROLL - 1) * RL < r1; r += (long long)GN_UNROLL * RL) {
     Half8 v[GN_UNROLL];
 #pragma unroll
     for (int u = 0; u < GN_UNROLL; u++) v[u] = ld_stream(base + (r + (long long)u * RL) * ld);
 #pragma unroll
-    for (int u = 0; u < GN_UNROLL; u++) *reinterpret_cast<Half8*>(yb + (r + (long long)u * RL) * C) = xform(v[u]);
+    for (int u = 0; u < GN_UNROLL; u++) put(r + (long long)u * RL, xform(v[u]));
   }
-  for (; r < r1; r += RL) *reinterpret_cast<Half8*>(yb + r * C) = xform(ld_stream(base + r * ld));
+  for (; r < r1; r += RL) put(r, xform(ld_stream(base + r * ld)));
+  if (remote) __threadfence_system();
 }
 
 // ---- LayerNorm: LPR lanes per row (32/LPR rows per warp pass), VPL 16-byte vectors per lane ------------------
@@ -355,9 +370,25 @@ extern "C" int hi3d_groupnorm_sums(const void* x1, int C1, const void* x2, int C
 extern "C" int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
                                     const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
                                     int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* stream) {
+  return hi3d_groupnorm_apply_halo(x1, C1, x2, C2, n_samples, rows_per_sample, sums, count_rows, gamma, beta, eps, apply_silu,
+                                   y, y_sample_rows, y_row_off, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
+                                         const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
+                                         int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* y_prev_rank,
+                                         void* y_next_rank, int64_t frame_rows, void* stream) {
   if (!x2) C2 = 0;
   int rc = gn_check(x1, C1, x2, C2, n_samples, rows_per_sample, "hi3d_groupnorm_apply");
   if (rc) return rc;
+  if ((y_prev_rank || y_next_rank) &&
+      (frame_rows <= 0 || rows_per_sample % frame_rows || y_sample_rows != rows_per_sample + 2 * frame_rows ||
+       y_row_off != frame_rows || ((uintptr_t)y_prev_rank & 15) || ((uintptr_t)y_next_rank & 15))) {
+    set_error("hi3d_groupnorm_apply_halo: the peer halo stores need y = [n, T_local + 2, frame_rows, C] with y_row_off = "
+              "frame_rows (rows %lld, frame_rows %lld, y_sample_rows %lld, y_row_off %lld)", (long long)rows_per_sample,
+              (long long)frame_rows, (long long)y_sample_rows, (long long)y_row_off);
+    return -2;
+  }
   if (!sums || !gamma || !beta || !y || ((uintptr_t)y & 15) || count_rows <= 0) {
     set_error("hi3d_groupnorm_apply: bad arguments");
     return -2;
@@ -378,7 +409,8 @@ extern "C" int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int 
   if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_apply: too many slabs"); return -2; }
   gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
       (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, sums,
-      (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off);
+      (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off,
+      (__half*)y_prev_rank, (__half*)y_next_rank, frame_rows);
   return check_launch("hi3d_groupnorm_apply");
 }
 

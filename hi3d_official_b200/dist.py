@@ -54,40 +54,42 @@ def gather_to_rank0(x: torch.Tensor) -> Optional[torch.Tensor]:
     return torch.cat(bufs, 0) if rank == 0 else None
 
 
-# ---- frame-sharded exchanges ------------------------------------------------------------------------------------------
-def allgather_frames(local: torch.Tensor, T: int) -> torch.Tensor:
-    """local: [b, t_local, ...] rows of this rank's frames -> [b, T, ...] with every rank's frames in frame order
-    (the K/V all-gather before each temporal-attention block)."""
-    rank, ws = world()
-    if ws == 1:
-        return local
-    if T % ws:
-        raise ValueError("frame sharding needs T divisible by the world size")
-    bufs = [torch.empty_like(local) for _ in range(ws)]
-    dist.all_gather(bufs, local.contiguous())
-    return torch.cat(bufs, dim=1)
-
-
-def halo_exchange(local: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """local: [b, t_local, ...].  Returns (prev, next): the last frame of rank-1 and the first frame of rank+1
-    (zeros at the clip boundaries = the Conv3d zero padding at t = -1 and t = T, openaimodel.py:252-261)."""
-    rank, ws = world()
-    first, last = local[:, :1].contiguous(), local[:, -1:].contiguous()
-    prev, nxt = torch.zeros_like(first), torch.zeros_like(last)
-    if ws == 1:
-        return prev, nxt
-    ops = []
-    if rank + 1 < ws:
-        ops += [dist.P2POp(dist.isend, last, rank + 1), dist.P2POp(dist.irecv, nxt, rank + 1)]
-    if rank > 0:
-        ops += [dist.P2POp(dist.isend, first, rank - 1), dist.P2POp(dist.irecv, prev, rank - 1)]
-    for w in dist.batch_isend_irecv(ops):
-        w.wait()
-    return prev, nxt
-
-
-def allreduce_gn_partials(partials: torch.Tensor) -> torch.Tensor:
-    """partials: [b, 32, 2] (sum, sumsq) of this rank's frames -> totals over all frames of the clip."""
+# ---- frame-sharded exchanges, NCCL / gloo form -----------------------------------------------------------------------
+# Used by the launch plan (unet._Plan) when HI3D_SHARD_EXCHANGE=nccl; the default on B200 is the peer-memory form
+# (peer.py + the sharded kernels), which needs no collective library on the step's path.  These operate in place on the
+# plan's own buffers and are backend-agnostic, so tests/test_dist_cpu.py runs exactly this code under 2-rank gloo.
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """[B, 32, 2] (sum, sumsq) GroupNorm partials of this rank's frames -> totals over all frames of the clip."""
     if world()[1] > 1:
-        dist.all_reduce(partials, op=dist.ReduceOp.SUM)
-    return partials
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def halo_exchange_(g: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
+    """g: [B, T_local + 2, X] haloed GroupNorm output (frames 1..T_local are local).  Frame 0 <- last local frame of
+    rank-1, frame T_local+1 <- first local frame of rank+1, zeros at the clip boundaries (the Conv3d zero padding at
+    t = -1 and t = T, openaimodel.py:252-261)."""
+    T = g.shape[1] - 2
+    ops_ = []
+    for b in range(g.shape[0]):
+        if rank > 0:
+            ops_ += [dist.P2POp(dist.isend, g[b, 1], rank - 1), dist.P2POp(dist.irecv, g[b, 0], rank - 1)]
+        else:
+            g[b, 0].zero_()
+        if rank + 1 < world_size:
+            ops_ += [dist.P2POp(dist.isend, g[b, T], rank + 1), dist.P2POp(dist.irecv, g[b, T + 1], rank + 1)]
+        else:
+            g[b, T + 1].zero_()
+    if ops_:
+        for wk in dist.batch_isend_irecv(ops_):
+            wk.wait()
+    return g
+
+
+def gather_frames_(local: torch.Tensor, full: torch.Tensor, B: int, rows_local: int, world_size: int) -> torch.Tensor:
+    """local [B * rows_local, X] (this rank's frames of every clip) -> full [B * world * rows_local, X] in frame order:
+    one all-gather per clip (the K/V all-gather before each temporal-attention block)."""
+    n = rows_local
+    for b in range(B):
+        dist.all_gather_into_tensor(full[b * n * world_size:(b + 1) * n * world_size], local[b * n:(b + 1) * n])
+    return full

@@ -155,12 +155,16 @@ def groupnorm_sums(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int,
 
 def groupnorm_apply(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int, rows_per_sample: int, sums: torch.Tensor,
                     count_rows: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, y: torch.Tensor,
-                    y_sample_rows: int = 0, y_row_off: int = 0):
+                    y_sample_rows: int = 0, y_row_off: int = 0, y_prev: Optional[int] = None, y_next: Optional[int] = None,
+                    frame_rows: int = 0):
+    """y_prev / y_next: raw device pointers of the SAME haloed buffer on the ranks holding the previous / next frames
+    (peer memory); the boundary frames are then also stored into their halo slots (hi3d_groupnorm_apply_halo)."""
     _chk16(x1, "x1"); _chk16(y, "y"); _chk32(sums, "sums"); _chk32(gamma, "gamma"); _chk32(beta, "beta")
     c2 = 0 if x2 is None else x2.shape[-1]
-    N.check(N.load().hi3d_groupnorm_apply(x1.data_ptr(), x1.shape[-1], _ptr(x2), c2, n_samples, rows_per_sample,
-                                          sums.data_ptr(), count_rows, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
-                                          y.data_ptr(), y_sample_rows, y_row_off, _stream()), "hi3d_groupnorm_apply")
+    N.check(N.load().hi3d_groupnorm_apply_halo(x1.data_ptr(), x1.shape[-1], _ptr(x2), c2, n_samples, rows_per_sample,
+                                               sums.data_ptr(), count_rows, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
+                                               y.data_ptr(), y_sample_rows, y_row_off, y_prev, y_next, frame_rows, _stream()),
+            "hi3d_groupnorm_apply")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, M: int,
@@ -184,6 +188,13 @@ def temporal_attention_d64(qkv: torch.Tensor, B: int, T: int, S: int, heads: int
     _chk16(qkv, "qkv"); _chk16(out, "out")
     N.check(N.load().hi3d_temporal_attention_d64(qkv.data_ptr(), B, T, S, heads, scale, out.data_ptr(), _stream()),
             "hi3d_temporal_attention_d64")
+
+
+def temporal_attention_d64_sharded(qkv_sb, out_sb, rank: int, world: int, B: int, T_local: int, S: int, heads: int,
+                                   scale: float = 0.125):
+    """qkv_sb / out_sb: peer.SymmBuffer of the q|k|v and output token matrices (same layout on every rank)."""
+    N.check(N.load().hi3d_temporal_attention_d64_sharded(qkv_sb.ptr_array, out_sb.ptr_array, rank, world, B, T_local, S, heads,
+                                                         scale, _stream()), "hi3d_temporal_attention_d64_sharded")
 
 
 def softmax_rows(s: torch.Tensor, rows: int, L: int, scale: float):

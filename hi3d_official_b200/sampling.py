@@ -219,9 +219,10 @@ class _FusedState:
         self.scale = scale.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
         self.key = None
         self.cc = self.cuc = None
-        # CUDA-graph replay of the whole step (pre -> ~750 launches -> post): static I/O buffers + one graph
-        # (not with frame sharding: the NCCL exchanges are issued eagerly)
-        self.use_graph = os.environ.get("HI3D_CUDA_GRAPH", "1") != "0" and shard is None
+        # CUDA-graph replay of the whole step (pre -> ~750 launches -> post): static I/O buffers + one graph.  Frame-sharded
+        # plans are captured too when their exchanges are peer-memory kernels (every rank replays the same graph, the flag
+        # barriers inside it keep the ranks in step); with NCCL exchanges the step stays eager.
+        self.use_graph = os.environ.get("HI3D_CUDA_GRAPH", "1") != "0" and (shard is None or self.plan.exchange_mode == "peer")
         self._graph = None
         self._gx = torch.zeros(F_, 4, H, W, dtype=torch.float32, device=dev)
         self._gxo = torch.zeros_like(self._gx)

@@ -47,13 +47,17 @@ class _ParamTree(nn.Module):
 
 
 class Arena:
-    """Named scratch buffers: one allocation per tag, sized to the largest request, handed out as views."""
+    """Named scratch buffers: one allocation per tag, sized to the largest request, handed out as views.
+    Tags listed in `symm_tags` are allocated as symmetric peer memory (peer.SymmBuffer): every rank of a frame-sharded
+    run holds the same buffer at the same tag and can address the other ranks' copies (`peers(tag)`)."""
 
-    def __init__(self, device):
+    def __init__(self, device, peer_group=None, symm_tags=()):
         self.device = device
         self.req: Dict[str, int] = {}
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: List[Tuple[str, int, int, list]] = []
+        self.peer_group, self.symm_tags = peer_group, tuple(symm_tags)
+        self.symm: Dict[str, object] = {}
 
     def want(self, tag: str, rows: int, cols: int) -> "LazyBuf":
         n = rows * cols
@@ -61,9 +65,19 @@ class Arena:
         return LazyBuf(self, tag, rows, cols)
 
     def materialise(self):
-        for tag, n in self.req.items():
+        for tag, n in sorted(self.req.items()):           # sorted: every rank allocates the symmetric tags in the same order
             if tag not in self.bufs or self.bufs[tag].numel() < n:
-                self.bufs[tag] = torch.zeros(n, dtype=F16, device=self.device)
+                if self.peer_group is not None and tag in self.symm_tags:
+                    sb = self.peer_group.alloc(n * 2)
+                    self.symm[tag] = sb
+                    self.bufs[tag] = sb.view(F16)[:n]
+                else:
+                    self.bufs[tag] = torch.zeros(n, dtype=F16, device=self.device)
+
+    def peers(self, tag: str):
+        """peer.SymmBuffer of a symmetric tag (views of a tag start at offset 0, so the peers' base pointers address the same
+        rows on every rank)."""
+        return self.symm[tag]
 
     def get(self, tag: str, rows: int, cols: int) -> torch.Tensor:
         return self.bufs[tag][: rows * cols].view(rows, cols)
@@ -259,7 +273,17 @@ class _Plan:
         self.dev = net.device
         self.engine = net.engine
         self.attn_engine = os.environ.get("HI3D_ATTN_ENGINE", net.engine)
-        self.arena = Arena(self.dev)
+        # frame sharding: how the three cross-frame ops exchange data.  "peer" (default) = peer-memory loads /
+        # stores inside the consuming / producing kernels + one flag-barrier kernel per exchange point, CUDA-graph
+        # capturable; "nccl" = torch.distributed collectives (dist.py), eager.
+        self.exchange_mode = os.environ.get("HI3D_SHARD_EXCHANGE", "peer") if self.shard else None
+        if self.exchange_mode not in (None, "peer", "nccl"):
+            raise ValueError(f"HI3D_SHARD_EXCHANGE={self.exchange_mode!r}: expected 'peer' or 'nccl'")
+        self.peer = None
+        if self.exchange_mode == "peer":
+            from . import peer as _peer
+            self.peer = _peer.get_group(self.rank, self.world, self.dev)
+        self.arena = Arena(self.dev, self.peer, ("qkv", "att", "ghalo") if self.peer is not None else ())
         self.steps: List = []          # main per-step launch list (built lazily as (kind, builder) then baked)
         self._build: List = []         # deferred builders, run after the arena is materialised
         self._cond_build: List = []
@@ -283,6 +307,7 @@ class _Plan:
         self.gn_ws = ops.groupnorm_ws(N, dev)
         self.frame_idx = torch.arange(T, dtype=torch.float32, device=dev) + float(self.rank * T)   # global frame ids
         self.gn_sums = torch.zeros(self.B, 32, 2, dtype=torch.float32, device=dev)               # sharded temporal GN
+        self.gn_sums_local = torch.zeros(self.B, 32, 2, dtype=torch.float32, device=dev)
         self._cond_key = None
         self._compile()
 
@@ -475,53 +500,42 @@ class _Plan:
             self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv2"][0], out, M, mode=ops.ROWS_TEMPORAL, geom=geo,
                        bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"])
             return
-        # frames sharded over ranks: (sum, sumsq) all-reduce for the (T,H,W) statistics, GN output
-        # written into a haloed [B, T+2, HW, C] buffer, one-frame halo exchange, 3-tap conv over the haloed source.
+        # frames sharded over ranks: the (T,H,W) statistics need the (sum, sumsq) of every rank, the GN
+        # output goes into a haloed [B, T+2, HW, C] buffer whose halo frames come from the neighbour ranks, and the 3-tap
+        # conv reads the haloed source.
         gh = A.want("ghalo", B * (T + 2) * HW, cout)
         geo = dict(Ho=HW, Wo=1, T=T, Tin=T + 2, t_off=1)
+        r, R = self.rank, self.world
         for src, (gg, bb), wkey, dst, extra in (
                 (xs, (g3, b3), "conv1", hbuf, dict(rowbias=emb2, rb_div=HW, rb_mod=N)),
                 (hbuf, (g4, b4), "conv2", out, dict(residual=xs, blend_x=xs, alpha=P[n + "alpha"]))):
-            self._call(bl, lambda src=src: ops.groupnorm_sums(src.t, None, B, T * HW, self.gn_sums, ws), kind="groupnorm",
-                       bytes=2.0 * M * cout)
-            self._call(bl, lambda: self._allreduce(self.gn_sums), kind="nccl")
-            self._call(bl, lambda src=src, gg=gg, bb=bb: ops.groupnorm_apply(
-                src.t, None, B, T * HW, self.gn_sums, self.Tg * HW, gg, bb, 1e-5, True, gh.t, (T + 2) * HW, HW),
-                kind="groupnorm", bytes=4.0 * M * cout)
-            self._call(bl, lambda: self._halo_exchange(gh.t.view(B, T + 2, HW * cout)), kind="nccl")
+            if self.peer is not None:
+                # peer memory: partial sums ride on the exchange kernel (all-reduce in one launch); the halo frames are
+                # stored into the neighbours' buffers by the apply kernel itself; a second exchange orders those stores
+                # before the conv (and, with the first, protects the single ghalo buffer from the next writer)
+                pg = self.peer
+                self._call(bl, lambda src=src: ops.groupnorm_sums(src.t, None, B, T * HW, self.gn_sums_local, ws),
+                           kind="groupnorm", bytes=2.0 * M * cout)
+                self._call(bl, lambda: pg.exchange(self.gn_sums_local, self.gn_sums), kind="exchange")
+
+                def apply(src=src, gg=gg, bb=bb):
+                    sb = A.peers("ghalo")
+                    return ops.groupnorm_apply(src.t, None, B, T * HW, self.gn_sums, self.Tg * HW, gg, bb, 1e-5, True, gh.t,
+                                               (T + 2) * HW, HW, y_prev=sb.peer(r - 1), y_next=sb.peer(r + 1) if r + 1 < R else None,
+                                               frame_rows=HW)
+                self._call(bl, apply, kind="groupnorm", bytes=4.0 * M * cout)
+                self._call(bl, lambda: pg.exchange(), kind="exchange")
+            else:
+                from . import dist as D
+                self._call(bl, lambda src=src: ops.groupnorm_sums(src.t, None, B, T * HW, self.gn_sums, ws), kind="groupnorm",
+                           bytes=2.0 * M * cout)
+                self._call(bl, lambda: D.allreduce_sum_(self.gn_sums), kind="nccl")
+                self._call(bl, lambda src=src, gg=gg, bb=bb: ops.groupnorm_apply(
+                    src.t, None, B, T * HW, self.gn_sums, self.Tg * HW, gg, bb, 1e-5, True, gh.t, (T + 2) * HW, HW),
+                    kind="groupnorm", bytes=4.0 * M * cout)
+                self._call(bl, lambda: D.halo_exchange_(gh.t.view(B, T + 2, HW * cout), r, R), kind="nccl")
             self._gemm(bl, lambda: ops.temporal_taps(gh.t), P[q + wkey][0], dst, M, mode=ops.ROWS_TEMPORAL, geom=geo,
                        bias=P[q + wkey][1], **extra)
-
-    # ---- frame-sharding collectives (torch.distributed / NCCL on the current stream) -----------------------------------
-    def _allreduce(self, t: torch.Tensor):
-        import torch.distributed as dist
-        dist.all_reduce(t)
-
-    def _halo_exchange(self, g: torch.Tensor):
-        """g: [B, T+2, HW*C] haloed GN output; frame 0 <- last frame of rank-1, frame T+1 <- first frame of rank+1,
-        zeros at the clip boundaries (the Conv3d zero padding at t = -1 and t = T, openaimodel.py:252-261)."""
-        import torch.distributed as dist
-        r, R, T = self.rank, self.world, self.T
-        ops_ = []
-        for b in range(g.shape[0]):
-            if r > 0:
-                ops_ += [dist.P2POp(dist.isend, g[b, 1], r - 1), dist.P2POp(dist.irecv, g[b, 0], r - 1)]
-            else:
-                g[b, 0].zero_()
-            if r + 1 < R:
-                ops_ += [dist.P2POp(dist.isend, g[b, T], r + 1), dist.P2POp(dist.irecv, g[b, T + 1], r + 1)]
-            else:
-                g[b, T + 1].zero_()
-        for wk in dist.batch_isend_irecv(ops_):
-            wk.wait()
-
-    def _gather_frames(self, local: torch.Tensor, full: torch.Tensor, rows_per_clip_local: int):
-        """local [B * T*HW, X] -> full [B * Tg*HW, X] (frame order) : one all-gather per clip (the K/V all-gather
-        before each temporal-attention block)."""
-        import torch.distributed as dist
-        n = rows_per_clip_local
-        for b in range(self.B):
-            dist.all_gather_into_tensor(full[b * n * self.world:(b + 1) * n * self.world], local[b * n:(b + 1) * n])
 
     def _transformer(self, L: Layer, x: LazyBuf, out: LazyBuf, h: int, w: int):
         """SpatialVideoTransformer.forward (video_attention.py:230-301), see module docstring for the folds."""
@@ -581,11 +595,21 @@ class _Plan:
             if self.shard is None:
                 self._call(bl, lambda: ops.temporal_attention_d64(qkv.t, B, T, HW, heads, att.t), kind="temporal_attention",
                            flops=4.0 * N * HW * T * C, bytes=8.0 * M * C)
+            elif self.peer is not None:
+                # pixel-strip sharding over peer memory: this rank attends pixel strip `rank` for ALL Tg frames, reading the
+                # other ranks' q|k|v rows from their buffers and storing their frames' outputs into their `att` buffers
+                pg = self.peer
+                self._call(bl, lambda: pg.exchange(), kind="exchange")           # every rank's q|k|v is written
+                self._call(bl, lambda: ops.temporal_attention_d64_sharded(A.peers("qkv"), A.peers("att"), self.rank, self.world,
+                                                                          B, T, HW, heads),
+                           kind="temporal_attention", flops=4.0 * N * HW * self.Tg * C, bytes=8.0 * M * C)
+                self._call(bl, lambda: pg.exchange(), kind="exchange")           # every rank's `att` rows have arrived
             else:
-                # all-gather q|k|v rows of every rank (frame order), attend over all Tg frames, keep the local frames
+                # NCCL form: all-gather q|k|v rows of every rank (frame order), attend over all Tg frames, keep the local frames
+                from . import dist as D
                 Tg, r = self.Tg, self.rank
                 qkv_f, att_f = A.want("qkv_full", B * Tg * HW, 3 * C), A.want("att_full", B * Tg * HW, C)
-                self._call(bl, lambda: self._gather_frames(qkv.t, qkv_f.t, T * HW), kind="nccl")
+                self._call(bl, lambda: D.gather_frames_(qkv.t, qkv_f.t, B, T * HW, self.world), kind="nccl")
                 self._call(bl, lambda: ops.temporal_attention_d64(qkv_f.t, B, Tg, HW, heads, att_f.t),
                            kind="temporal_attention", flops=4.0 * B * Tg * HW * Tg * C, bytes=8.0 * B * Tg * HW * C)
 

@@ -24,6 +24,7 @@ extern "C" {
 #endif
 
 #define HI3D_MAX_SEGS 24
+#define HI3D_MAX_PEERS 16   /* ranks of one frame-sharded video (16 frames) */
 
 /* library ------------------------------------------------------------------------------------ */
 int hi3d_abi_version(void);
@@ -132,6 +133,17 @@ int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int n_s
                          const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
                          int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* stream);
 
+/* hi3d_groupnorm_apply for frame-sharded runs with the one-frame halo exchange of the temporal (3,1,1) conv fused into its
+ * stores: y = [n, T_local + 2, frame_rows, C] (y_sample_rows = (T_local + 2) * frame_rows, y_row_off = frame_rows); the first
+ * local frame is also stored into the trailing halo slot of `y_prev_rank` (the same buffer of the rank holding the previous
+ * frames, mapped through hi3d_symm_open) and the last local frame into the leading slot of `y_next_rank`; NULL at the clip
+ * boundaries (those slots stay zero = the Conv3d zero padding, openaimodel.py:252-261).  A hi3d_peer_exchange must
+ * separate this launch from the conv that reads the halo slots. */
+int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
+                              const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
+                              int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* y_prev_rank,
+                              void* y_next_rank, int64_t frame_rows, void* stream);
+
 /* LayerNorm over the last dim C (<= 2560, multiple of 8) of [M, C] fp16 (+ optional broadcast add before the norm:
  * x + addvec[((m / add_div) % add_mod), :], the `x_mix = x + emb` of video_attention.py:286-287).
  * Replaces nn.LayerNorm at attention.py:520-522, video_attention.py:51,79,93-94.  y fp16 [M, C]. */
@@ -163,6 +175,15 @@ int hi3d_attention_tc5_set_variant(int variant);
  * qkv fp16 [B*T*S, 3*C]; out fp16 [B*T*S, C].  Replaces attn1 core at video_attention.py:125. */
 int hi3d_temporal_attention_d64(const void* qkv, int B, int T, int S, int heads, float scale, void* out,
                                 void* stream);
+
+/* Frame-sharded form (the reference has no multi-GPU inference, README.md:56-64): rank r owns frames
+ * [r*T_local, (r+1)*T_local) of every clip in its own qkv / out buffers (layout as above with T = T_local) and computes
+ * pixel strip r of all T_local*world frames: q|k|v rows of the other ranks' frames are READ from `qkv_of_rank[owner]` and the
+ * output rows of their frames are STORED into `out_of_rank[owner]` (device pointers of the peers' buffers mapped with
+ * hi3d_symm_open; entry [rank] = the local buffers).  One hi3d_peer_exchange before (all q|k|v written) and one after (all
+ * outputs stored) order it against the producing / consuming GEMMs. */
+int hi3d_temporal_attention_d64_sharded(void* const* qkv_of_rank, void* const* out_of_rank, int rank, int world, int B,
+                                        int T_local, int S, int heads, float scale, void* stream);
 
 /* Row softmax in place on fp16 [rows, L] (scores * scale), and 2-D transpose [R, Cc] -> [Cc, R] (fp16):
  * building blocks of the VAE single-head d=512 attention (model.py:180-195) on top of hi3d_gemm. */
@@ -209,6 +230,25 @@ int hi3d_nhwc_to_nchw(const void* in, int in_ld, int N, int C, int H, int W, flo
  * out fp32 NCHW [N, C, H, W]. */
 int hi3d_gaussian_sample(const void* moments, int ld, const float* noise, int N, int C, int H, int W, float scale,
                          float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Peer memory for the frame-sharded step (one process per GPU).  No reference counterpart.
+ * --------------------------------------------------------------------------------------------- */
+/* Symmetric buffers: hi3d_symm_alloc = cudaMalloc + zero fill + cudaIpcGetMemHandle (handle64: 64 bytes the host ships to
+ * the other ranks, e.g. with torch.distributed.all_gather_object); hi3d_symm_open maps a peer's buffer into this process
+ * (cudaIpcOpenMemHandle, enabling peer access); hi3d_symm_close / hi3d_symm_free undo them. */
+int hi3d_symm_alloc(int64_t bytes, void** ptr, void* handle64);
+int hi3d_symm_open(const void* handle64, void** ptr);
+int hi3d_symm_close(void* ptr);
+int hi3d_symm_free(void* ptr);
+/* Size of one rank's exchange area (flags + payload slots + epoch word) for hi3d_peer_exchange. */
+int64_t hi3d_peer_xchg_bytes(int world);
+/* One exchange point of the sharded step, a single-CTA kernel on `stream`: every rank announces a new epoch in its slot of
+ * every peer's flag array and waits until all peers have announced it -- everything the ranks stored into each other's
+ * buffers before this point is visible after it.  With n > 0 (<= 1024) it is also an all-reduce: out[j] = sum over ranks of
+ * payload[j] in rank order (the [B, 32, 2] partial sums of the temporal GroupNorm, video_model.py:71-76).  xchg[r] = rank
+ * r's exchange area (zero-initialised symmetric memory); every rank must issue the same sequence of exchanges. */
+int hi3d_peer_exchange(void* const* xchg, int rank, int world, const float* payload, int n, float* out, void* stream);
 
 /* One-time weight packing (device -> device), the C twin of hi3d_official_b200/pack.py for hosts without torch:
  * reference layouts as stored in the checkpoints -- nn.Linear [Co, Ci] (taps = 1; attention.py:269-278, 87-113),

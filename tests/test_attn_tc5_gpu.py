@@ -20,8 +20,8 @@ def kernel_variant(request):
     _native.check(lib.hi3d_attention_tc5_set_variant(variant), "set_variant")
     _native.check(lib.hi3d_attention_tc5_set_exp_emulation(emu), "set_exp_emulation")
     yield request.param
-    _native.check(lib.hi3d_attention_tc5_set_variant(0), "set_variant")
-    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(1), "set_exp_emulation")
+    _native.check(lib.hi3d_attention_tc5_set_variant(1), "set_variant")            # back to the production defaults
+    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(0), "set_exp_emulation")
 
 
 def ref_attn(qkv, n_img, L, heads):

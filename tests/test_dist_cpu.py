@@ -1,6 +1,7 @@
 """world_size-2 gloo tests of the multi-GPU host logic (hi3d_official_b200/dist.py): sharding, the three
-frame-sharded exchanges (K/V all-gather, temporal-conv halo, GroupNorm partial all-reduce) reproduce the
-unsharded oracle ops bit-for-bit / to fp32 round-off, and the max-over-ranks timing reduce."""
+frame-sharded exchanges in the in-place form the launch plan calls (unet._Plan with HI3D_SHARD_EXCHANGE=nccl: K/V
+all-gather, temporal-conv halo, GroupNorm partial all-reduce) reproduce the unsharded oracle ops bit-for-bit / to fp32
+round-off, and the max-over-ranks timing reduce."""
 import os
 
 import torch
@@ -20,8 +21,11 @@ def _worker(rank, ws, port, q):
         x = torch.randn(b, T, hw, c)                       # full clip, identical on every rank
         mine = D.shard_range(T, rank, ws)
         loc = x[:, mine.start:mine.stop].contiguous()
-        # (i) all-gather for temporal attention
-        full = D.allgather_frames(loc, T)
+        # (i) all-gather for temporal attention: the plan's in-place form on [B * rows, X] token matrices
+        tl = len(mine)
+        full2 = torch.empty(b * T * hw, c)
+        D.gather_frames_(loc.reshape(b * tl * hw, c), full2, b, tl * hw, ws)
+        full = full2.view(b, T, hw, c)
         assert torch.equal(full, x)
         q_ = loc.permute(0, 2, 1, 3).reshape(b * hw, len(mine), c)
         kv = full.permute(0, 2, 1, 3).reshape(b * hw, T, c)
@@ -30,15 +34,18 @@ def _worker(rank, ws, port, q):
         assert torch.allclose(att, ref[:, mine.start:mine.stop], atol=1e-6)
         # (ii) halo for the (3,1,1) temporal conv
         w = torch.randn(c, c, 3, 1, 1) * 0.05
-        prev, nxt = D.halo_exchange(loc)
-        ext = torch.cat([prev, loc, nxt], 1).permute(0, 3, 1, 2)[..., None]       # b c t hw 1
+        gh = torch.full((b, tl + 2, hw * c), float("nan"))                        # the plan's haloed buffer [B, T_local + 2, X]
+        gh[:, 1:tl + 1] = loc.reshape(b, tl, hw * c)
+        D.halo_exchange_(gh, rank, ws)
+        assert not torch.isnan(gh).any()
+        ext = gh.view(b, tl + 2, hw, c).permute(0, 3, 1, 2)[..., None]            # b c t hw 1
         y_loc = F.conv3d(ext, w)                                                 # valid conv over the halo
         y_ref = F.conv3d(x.permute(0, 3, 1, 2)[..., None], w, padding=(1, 0, 0))
         assert torch.allclose(y_loc, y_ref[:, :, mine.start:mine.stop], atol=1e-5)
         # (iii) GroupNorm over (C/32, T, H, W) from all-reduced partial sums
         g = loc.reshape(b, -1, 32, c // 32)
         part = torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1)             # b 32 2
-        tot = D.allreduce_gn_partials(part.clone())
+        tot = D.allreduce_sum_(part.clone())
         cnt = T * hw * (c // 32)
         mean = tot[..., 0] / cnt
         var = tot[..., 1] / cnt - mean ** 2

@@ -117,8 +117,8 @@ def main():
                         report(f"{e} spatial attention L={L} heads={heads} variant={var} emu={emu}/4",
                                timeit(lambda: ops.attention_d64(qkv, N, L, heads, out, engine=e), once=args.once),
                                4.0 * N * L * L * C)
-                _native.load().hi3d_attention_tc5_set_variant(0)
-                _native.load().hi3d_attention_tc5_set_exp_emulation(1)
+                _native.load().hi3d_attention_tc5_set_variant(1)
+                _native.load().hi3d_attention_tc5_set_exp_emulation(0)
             report(f"temporal attention S={L} heads={heads}",
                    timeit(lambda: ops.temporal_attention_d64(qkv, 2, T, L, heads, out), once=args.once), 4.0 * N * L * T * C,
                    8.0 * M * C)
