@@ -137,7 +137,7 @@ int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int n_s
  * stores: y = [n, T_local + 2, frame_rows, C] (y_sample_rows = (T_local + 2) * frame_rows, y_row_off = frame_rows); the first
  * local frame is also stored into the trailing halo slot of `y_prev_rank` (the same buffer of the rank holding the previous
  * frames, mapped through hi3d_symm_open) and the last local frame into the leading slot of `y_next_rank`; NULL at the clip
- * boundaries (those slots stay zero = the Conv3d zero padding, openaimodel.py:252-261).  A hi3d_peer_exchange must
+ * boundaries: the local halo slot is then zero-filled (the Conv3d zero padding, openaimodel.py:252-261).  A hi3d_peer_exchange must
  * separate this launch from the conv that reads the halo slots. */
 int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
                               const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,

@@ -213,3 +213,36 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["config"]["reference_latent_override"] == 8 and d["sampler_steps_timed"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_video_io_and_svd_widening(tmp_path):
+    """tensor2vid / export_to_video (vtdm/util.py:12-49) and the 8 -> 17 channel / 768 -> 512 checkpoint surgery
+    (tool_make_init_svd_to_vid2vid.py:40-61) against their definitions."""
+    import numpy as np
+    from hi3d_official_b200 import configs, spec, video_io
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 16), torch.linspace(-1, 1, 24), indexing="ij")
+    v = torch.stack([torch.stack([xx * (0.5 + 0.1 * f), yy, -xx * yy]) for f in range(4)], 1)[None]   # smooth (codec-friendly)
+    v = v + torch.tensor([1.3, -1.3, 0.0]).view(1, 3, 1, 1, 1) * 0.2                                 # some values clamp
+    ref = ((v.clone() * 0.5 + 0.5).clamp(0, 1).permute(0, 2, 3, 4, 1).reshape(4, 16, 24, 3).numpy() * 255).astype("uint8")
+    frames = video_io.tensor2vid(v.clone())
+    assert len(frames) == 4 and frames[0].shape == (16, 24, 3) and frames[0].dtype == np.uint8
+    assert all(np.array_equal(a, b) for a, b in zip(frames, ref))
+    mp4 = video_io.export_to_video(frames, str(tmp_path / "first.mp4"), fps=8)
+    back = video_io.read_video_frames(mp4)
+    assert len(back) == 4 and back[0].shape == (16, 24, 3)
+    assert np.abs(back[0].astype(int) - frames[0].astype(int)).mean() < 12          # lossy codec: same picture, not same bits
+    gif = video_io.export_to_video(frames, str(tmp_path / "first.mp4"), save_to_gif=True)
+    assert gif.endswith(".gif") and (tmp_path / "first.gif").exists()
+    # checkpoint surgery on reduced-width configs (same rule at every width)
+    kw1, kw2 = dict(configs.UNET_STAGE1, model_channels=32), dict(configs.UNET_STAGE2, model_channels=32)
+    sd1 = spec.synth_state_dict(spec.unet_param_shapes(spec.UNetConfig.from_kwargs(**kw1)), seed=3)
+    sd2 = spec.synth_state_dict(spec.unet_param_shapes(spec.UNetConfig.from_kwargs(**kw2)), seed=4)
+    pre = "model.diffusion_model."
+    wide = video_io.widen_svd_state_dict({pre + k: t for k, t in sd1.items()}, {pre + k: t for k, t in sd2.items()})
+    w_in, w1 = wide[pre + "input_blocks.0.0.weight"], sd1["input_blocks.0.0.weight"]
+    assert w_in.shape[1] == 17 and torch.equal(w_in[:, :4], w1[:, :4]) and torch.equal(w_in[:, 13:], w1[:, 4:])
+    assert not bool(w_in[:, 4:13].any())
+    le, l1 = wide[pre + "label_emb.0.0.weight"], sd1["label_emb.0.0.weight"]
+    assert le.shape[1] == 512 and not bool(le[:, :256].any()) and torch.equal(le[:, 256:], l1[:, 512:])
+    same = [k for k in sd1 if k not in ("input_blocks.0.0.weight", "label_emb.0.0.weight")]
+    assert all(torch.equal(wide[pre + k], sd1[k]) for k in same)
