@@ -113,9 +113,14 @@ class DiffusionEngine(nn.Module):
     # -- first stage (diffusion.py:117-150) -----------------------------------------------------------------------------
     @torch.no_grad()
     def decode_first_stage(self, z: torch.Tensor) -> torch.Tensor:
+        from .vae import VideoDecoder
         n_samples = default(self.en_and_decode_n_samples_a_time, z.shape[0])
-        outs = [self.first_stage_model.decode(z[i:i + n_samples], scale=1.0 / self.scale_factor)
-                for i in range(0, z.shape[0], n_samples)]
+        outs = []
+        for i in range(0, z.shape[0], n_samples):
+            zi = z[i:i + n_samples]
+            # diffusion.py:126-129: a temporal decoder is told how many frames the chunk holds
+            kw = {"timesteps": len(zi)} if isinstance(self.first_stage_model.decoder, VideoDecoder) else {}
+            outs.append(self.first_stage_model.decode(zi, scale=1.0 / self.scale_factor, **kw))
         return torch.cat(outs, 0) if len(outs) > 1 else outs[0]
 
     @torch.no_grad()

@@ -23,10 +23,16 @@ def pack_conv2d(w: torch.Tensor, cin_pad: Optional[int] = None, cout_pad: Option
     return out.reshape(cop, kh * kw * cip).to(F16).contiguous()
 
 
-def pack_conv3d_t(w: torch.Tensor) -> torch.Tensor:
-    """(Co, Ci, 3, 1, 1) temporal conv -> fp16 [Co, 3*Ci], K ordered (kt, ci) == ops.temporal_taps order."""
+def pack_conv3d_t(w: torch.Tensor, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None) -> torch.Tensor:
+    """(Co, Ci, 3, 1, 1) temporal conv -> fp16 [Co_p, 3*Ci_p], K ordered (kt, ci) == ops.temporal_taps order."""
     co, ci = w.shape[:2]
-    return w.float()[:, :, :, 0, 0].permute(0, 2, 1).reshape(co, 3 * ci).to(F16).contiguous()
+    if tuple(w.shape[2:]) != (3, 1, 1):
+        raise NotImplementedError(f"temporal conv kernel {tuple(w.shape[2:])}: only (3, 1, 1) (the SVD / Hi3D video_kernel_size) "
+                                  f"maps onto the frame-tap GEMM mode")
+    cip, cop = cin_pad or ci, cout_pad or co
+    out = torch.zeros(cop, 3, cip, dtype=torch.float32, device=w.device)
+    out[:co, :, :ci] = w.float()[:, :, :, 0, 0].permute(0, 2, 1)
+    return out.reshape(cop, 3 * cip).to(F16).contiguous()
 
 
 def pack_linear(w: torch.Tensor, cout_pad: Optional[int] = None) -> torch.Tensor:

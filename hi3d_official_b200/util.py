@@ -28,6 +28,10 @@ TARGET_ALIASES: Dict[str, str] = {
     "sgm.modules.diffusionmodules.sampling.DPMPP2MSampler": "hi3d_official_b200.sampling.DPMPP2MSampler",
     "sgm.models.autoencoder.AutoencoderKL": "hi3d_official_b200.vae.AutoencoderKL",
     "sgm.models.autoencoder.AutoencoderKLModeOnly": "hi3d_official_b200.vae.AutoencoderKLModeOnly",
+    # north_star's name for the first stage with the temporal decoder (no such class in the reference; its parts are
+    # AutoencodingEngineLegacy + temporal_ae.VideoDecoder)
+    "sgm.models.autoencoder.AutoencoderKLTemporal": "hi3d_official_b200.vae.AutoencoderKLTemporal",
+    "sgm.modules.autoencoding.temporal_ae.VideoDecoder": "hi3d_official_b200.vae.VideoDecoder",
     "sgm.modules.diffusionmodules.model.Encoder": "hi3d_official_b200.vae.Encoder",
     "sgm.modules.diffusionmodules.model.Decoder": "hi3d_official_b200.vae.Decoder",
     "sgm.modules.GeneralConditioner": "hi3d_official_b200.engine.PassThroughConditioner",

@@ -29,8 +29,8 @@ COUT_PAD = 8
 class _VAEPlan:
     """Launch plan for encoder or decoder at one (n, H, W)."""
 
-    def __init__(self, ae: "AutoencoderKL", which: str, n: int, H: int, W: int):
-        self.ae, self.which, self.n, self.H, self.W = ae, which, n, H, W
+    def __init__(self, ae: "AutoencoderKL", which: str, n: int, H: int, W: int, T: int = 0):
+        self.ae, self.which, self.n, self.H, self.W, self.T = ae, which, n, H, W, T
         self.P = ae._pack()
         self.dev = ae.device
         self.A = Arena(self.dev)
@@ -40,6 +40,8 @@ class _VAEPlan:
         self._pp = 0
         if which == "enc":
             self._compile_encoder()
+        elif which == "vdec":
+            self._compile_decoder(video=True)
         else:
             self._compile_decoder()
         self.A.materialise()
@@ -88,6 +90,35 @@ class _VAEPlan:
                        bias=b)
         else:
             self._gemm(lambda: ops.conv_taps([g2.t]), Wt, out, M, mode=ops.ROWS_CONV2D, geom=geo, bias=b, residual=x)
+        return out
+
+    def _video_resnet(self, pre: str, x: LazyBuf, cin: int, cout: int, h: int, w: int) -> LazyBuf:
+        """temporal_ae.VideoResBlock.forward (temporal_ae.py:62-81): the spatial ResnetBlock, then the `time_stack`
+        ResBlock(dims=3, kernel (3,1,1), no emb; openaimodel.py:328-354) on the (b, c, t, h, w) view -- GroupNorm over
+        (C/32, T, H, W), eps 1e-5 -- and x = a * time_stack(x) + (1 - a) * x with a = sigmoid(mix_factor): NOTE the blend
+        weighs the TEMPORAL branch (the UNet's AlphaBlender weighs the spatial one).  time_stack(x) = x + h, so
+        out = x + a h = (1 - a) x + a (x + h): the engine's blend epilogue with alpha_engine = 1 - a."""
+        xs = self._resnet(pre, x, cin, cout, h, w)
+        T, n = self.T, self.n
+        B, HW = n // T, h * w
+        M = n * HW
+        A = self.A
+        g, hb = A.want("gn", M, cout), A.want("h", M, cout)
+        out = self._nxt(M, cout)
+        q = pre + "time_stack."
+        geo = dict(Ho=HW, Wo=1, T=T)
+        a = self.P[pre + "mix_factor"]
+
+        def gn(src, key, dst):
+            gg, bb = self.P[key]
+            self._call(lambda: ops.groupnorm_silu(src.t, None, B, T * HW, gg, bb, 1e-5, True, dst.t, self.gn_ws))
+        gn(xs, q + "in_layers.0", g)
+        W1, b1 = self.P[q + "in_layers.2"]
+        self._gemm(lambda: ops.temporal_taps(g.t), W1, hb, M, mode=ops.ROWS_TEMPORAL, geom=geo, bias=b1)
+        gn(hb, q + "out_layers.0", g)
+        W2, b2 = self.P[q + "out_layers.3"]
+        self._gemm(lambda: ops.temporal_taps(g.t), W2, out, M, mode=ops.ROWS_TEMPORAL, geom=geo, bias=b2, residual=xs,
+                   blend_x=xs, alpha=1.0 - a)
         return out
 
     def _attn(self, pre: str, x: LazyBuf, C: int, h: int, w: int) -> LazyBuf:
@@ -150,9 +181,14 @@ class _VAEPlan:
         self._gemm(lambda: [ops.SegSpec(mom.t)], Wq, self.out, M, bias=bq)
         self.out_hw = (h, w)
 
-    def _compile_decoder(self):
-        """post_quant_conv (autoencoder.py:492) + Decoder.forward, model.py:715-748.  (H, W) are LATENT dims."""
+    def _compile_decoder(self, video: bool = False):
+        """post_quant_conv (autoencoder.py:492) + Decoder.forward, model.py:715-748.  (H, W) are LATENT dims.
+        video=True: temporal_ae.VideoDecoder (time_mode 'conv-only', temporal_ae.py:293-349) run as
+        Decoder.forward(z, timesteps=T): VideoResBlocks instead of ResnetBlocks, plain AttnBlock, AE3DConv as conv_out."""
         cfg, n, h, w, A = self.ae.cfg, self.n, self.H, self.W, self.A
+        if video and (self.T <= 0 or n % self.T):
+            raise ValueError(f"VideoDecoder: batch {n} is not a multiple of timesteps {self.T}")
+        resnet = self._video_resnet if video else self._resnet
         nres = len(cfg.ch_mult)
         self.xin = A.want("xin", n * h * w, CIN_PAD)
         zq = A.want("h", n * h * w, CIN_PAD)
@@ -161,13 +197,13 @@ class _VAEPlan:
         bi = cfg.ch * cfg.ch_mult[-1]
         cur = self._nxt(n * h * w, bi)
         self._conv(zq, "decoder.conv_in", cur, h, w, h, w)
-        cur = self._resnet("decoder.mid.block_1.", cur, bi, bi, h, w)
+        cur = resnet("decoder.mid.block_1.", cur, bi, bi, h, w)
         cur = self._attn("decoder.mid.attn_1.", cur, bi, h, w)
-        cur = self._resnet("decoder.mid.block_2.", cur, bi, bi, h, w)
+        cur = resnet("decoder.mid.block_2.", cur, bi, bi, h, w)
         for lvl in reversed(range(nres)):
             bo = cfg.ch * cfg.ch_mult[lvl]
             for b in range(cfg.num_res_blocks + 1):
-                cur = self._resnet(f"decoder.up.{lvl}.block.{b}.", cur, bi, bo, h, w)
+                cur = resnet(f"decoder.up.{lvl}.block.{b}.", cur, bi, bo, h, w)
                 bi = bo
             if lvl != 0:          # Upsample: nearest x2 + conv3x3 (model.py:67-71), fused into the gather
                 out = self._nxt(n * 4 * h * w, bi)
@@ -181,7 +217,16 @@ class _VAEPlan:
         g = A.want("gn", M, bi)
         self._gn(cur, "decoder.norm_out", h * w, g)
         self.out = A.want("img", M, COUT_PAD)
-        self._conv(g, "decoder.conv_out", self.out, h, w, h, w)
+        if not video:
+            self._conv(g, "decoder.conv_out", self.out, h, w, h, w)
+        else:
+            # AE3DConv (temporal_ae.py:84-108): the 2-D conv (output padded to one 64-wide K segment), then the Conv3d
+            # (3,1,1) over the frames of the (b, c, t, h, w) view as a frame-tap GEMM
+            mid = A.want("h", M, CIN_PAD)
+            self._conv(g, "decoder.conv_out", mid, h, w, h, w)
+            Wt, bt = self.P["decoder.conv_out.time_mix_conv"]
+            self._gemm(lambda: ops.temporal_taps(mid.t), Wt, self.out, M, mode=ops.ROWS_TEMPORAL,
+                       geom=dict(Ho=h * w, Wo=1, T=self.T), bias=bt)
         self.out_hw = (h, w)
 
     def run(self):
@@ -214,11 +259,11 @@ class AutoencoderKL(nn.Module):
             raise NotImplementedError("ckpt_path in the first-stage config: load weights with load_state_dict")
         self.cfg = VAEConfig.from_ddconfig(ddconfig, embed_dim)
         self.embed_dim = embed_dim
-        self.encoder, self.decoder = Encoder(), Decoder()
+        self.encoder, self.decoder = Encoder(), self._make_decoder()
         self.quant_conv, self.post_quant_conv = _ParamTree(), _ParamTree()
         roots = {"encoder": self.encoder, "decoder": self.decoder, "quant_conv": self.quant_conv,
                  "post_quant_conv": self.post_quant_conv}
-        for name, shp in vae_param_shapes(self.cfg).items():
+        for name, shp in self._param_shapes(ignored).items():
             root, rest = name.split(".", 1)
             roots[root].put(rest, nn.Parameter(torch.empty(shp), requires_grad=False))
         self._packed = None
@@ -228,6 +273,12 @@ class AutoencoderKL(nn.Module):
         # a parent's load_state_dict (DiffusionEngine.init_from_ckpt) recurses through _load_from_state_dict and never
         # reaches the override below: invalidate the packed weights / plans from a pre-hook as well
         self._register_load_state_dict_pre_hook(lambda *a, **k: self._invalidate())
+
+    def _param_shapes(self, kwargs: dict):
+        return vae_param_shapes(self.cfg)
+
+    def _make_decoder(self):
+        return Decoder()
 
     # -- lifecycle ----------------------------------------------------------------------------------------------------
     def _invalidate(self):
@@ -256,13 +307,23 @@ class AutoencoderKL(nn.Module):
             raise RuntimeError("hi3d_official_b200.AutoencoderKL computes only on CUDA; there is no CPU fallback")
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         P = {}
+        temporal = isinstance(self.decoder, VideoDecoder)
         for k in sd:
+            if k.endswith("mix_factor"):                       # temporal_ae.VideoResBlock: alpha = sigmoid(mix_factor)
+                P[k] = float(torch.sigmoid(sd[k].float()).item())
+                continue
             if not k.endswith(".weight"):
                 continue
             base = k[:-7]
             w, b = sd[k], sd[base + ".bias"]
             if w.dim() == 1:                                   # GroupNorm affine
                 P[base] = (w.float().contiguous(), b.float().contiguous())
+            elif base == "decoder.conv_out.time_mix_conv":     # AE3DConv's Conv3d (3,1,1) on out_ch channels
+                P[base] = (pack.pack_conv3d_t(w, cin_pad=CIN_PAD, cout_pad=COUT_PAD), pack.pack_bias(b, w.shape[0], COUT_PAD))
+            elif w.dim() == 5:                                 # time_stack convs (Co, Ci, 3, 1, 1)
+                P[base] = (pack.pack_conv3d_t(w), b.float().contiguous())
+            elif base == "decoder.conv_out" and temporal:      # feeds time_mix_conv: one 64-wide K segment per frame tap
+                P[base] = (pack.pack_conv2d(w, cout_pad=CIN_PAD), pack.pack_bias(b, w.shape[0], CIN_PAD))
             elif base.endswith("nin_shortcut"):
                 continue                                       # folded into conv2 below
             elif base in ("encoder.conv_in",):
@@ -287,10 +348,10 @@ class AutoencoderKL(nn.Module):
         self._packed = P
         return P
 
-    def _plan(self, which: str, n: int, H: int, W: int) -> _VAEPlan:
-        key = (which, n, H, W, self.engine)
+    def _plan(self, which: str, n: int, H: int, W: int, T: int = 0) -> _VAEPlan:
+        key = (which, n, H, W, self.engine, T)
         if key not in self._plans:
-            self._plans[key] = _VAEPlan(self, which, n, H, W)
+            self._plans[key] = _VAEPlan(self, which, n, H, W, T)
         return self._plans[key]
 
     # -- reference API --------------------------------------------------------------------------------------------------
@@ -328,16 +389,23 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def decode(self, z: torch.Tensor, scale: float = 1.0, **decoder_kwargs) -> torch.Tensor:
         """autoencoder.py:490-505 (post_quant_conv + decoder); returns NCHW in z's dtype."""
+        temporal = isinstance(self.decoder, VideoDecoder)
+        T = int(decoder_kwargs.pop("timesteps", 0)) if temporal else 0
         if decoder_kwargs:
-            raise NotImplementedError(f"decoder kwargs {list(decoder_kwargs)} (VideoDecoder) are not on the Hi3D path")
+            raise NotImplementedError(f"decoder kwargs {list(decoder_kwargs)}: the 2-D decoder takes none; the temporal "
+                                      f"decoder (AutoencoderKLTemporal) takes timesteps=T")
+        if temporal and T <= 0:
+            raise ValueError("the temporal decoder needs decode(z, timesteps=T) (diffusion.py:126-129)")
         if z.dtype not in (torch.float16, torch.float32):
             z = z.float()
         bs = self.max_batch_size or z.shape[0]
+        if temporal:                      # whole clips per launch plan
+            bs = max(T, bs // T * T)
         outs = []
         for i in range(0, z.shape[0], bs):
             zb = z[i:i + bs].contiguous()
             n, c, h, w = zb.shape
-            plan = self._plan("dec", n, h, w)
+            plan = self._plan("vdec", n, h, w, T) if temporal else self._plan("dec", n, h, w)
             ops.nchw_to_nhwc(zb, plan.xin.t.view(n, h, w, CIN_PAD), scale)
             plan.run()
             H, W = plan.out_hw
@@ -349,6 +417,36 @@ class AutoencoderKL(nn.Module):
     def forward(self, x: torch.Tensor, **kw):
         z = self.encode(x)
         return z, self.decode(z), {}
+
+
+class VideoDecoder(Decoder):
+    """Parameter tree of sgm.modules.autoencoding.temporal_ae.VideoDecoder (temporal_ae.py:293-349).  Its presence as
+    `first_stage_model.decoder` is what makes DiffusionEngine.decode_first_stage pass timesteps (diffusion.py:126-129)."""
+
+
+class AutoencoderKLTemporal(AutoencoderKL):
+    """The temporal first stage north_star calls "AutoencoderKLTemporal" (SURVEY F3 / §8f N1): the 2-D Encoder with the
+    temporal `VideoDecoder` of sgm/modules/autoencoding/temporal_ae.py (as in SVD's AutoencodingEngine config): every
+    ResnetBlock is a VideoResBlock (spatial block + (3,1,1) time_stack ResBlock + learned blend), conv_out is an AE3DConv;
+    `time_mode` 'conv-only' (plain AttnBlock), `video_kernel_size` [3, 1, 1].  decode(z, timesteps=T).
+    State-dict keys / shapes: spec.video_decoder_param_shapes (checked against the unmodified reference class)."""
+
+    def _param_shapes(self, kwargs: dict):
+        from .spec import video_decoder_param_shapes
+        vks = kwargs.get("video_kernel_size", [3, 1, 1])
+        k3 = tuple(vks) if not isinstance(vks, int) else (vks,) * 3
+        if k3 != (3, 1, 1):
+            raise NotImplementedError(f"video_kernel_size {vks}: only [3, 1, 1] (frame taps) is built; spatially extended "
+                                      f"temporal kernels would need (dt, dy, dx) taps in the implicit-GEMM engine")
+        if kwargs.get("time_mode", "conv-only") != "conv-only":
+            raise NotImplementedError("time_mode other than 'conv-only' (temporal attention inside the VAE) is not built")
+        shapes = vae_param_shapes(self.cfg)
+        out = type(shapes)((k, v) for k, v in shapes.items() if not k.startswith("decoder."))
+        out.update(video_decoder_param_shapes(self.cfg, k3))
+        return out
+
+    def _make_decoder(self):
+        return VideoDecoder()
 
 
 class AutoencoderKLModeOnly(AutoencoderKL):

@@ -48,6 +48,15 @@ def test_oracle_reproduces_reference_vae_fixture():
         torch.testing.assert_close(O.vae_decode(sd, fix["z_in"], scale_factor=1.0), fix["dec"], rtol=1e-4, atol=2e-4)
 
 
+def test_oracle_reproduces_reference_video_decoder_fixture():
+    """fixture from the unmodified temporal_ae.VideoDecoder (tools/make_golden.py --only-video)."""
+    fix = _load("vae_video_ch64.pt")
+    cfg = spec.VAEConfig.from_ddconfig(fix["ddconfig"], 4)
+    sd = spec.synth_state_dict(spec.video_decoder_param_shapes(cfg, tuple(fix["video_kernel_size"])), seed=fix["seed"])
+    with torch.no_grad():
+        torch.testing.assert_close(O.vae_video_decoder(sd, fix["z"], fix["T"]), fix["dec"], rtol=1e-4, atol=2e-4)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def _stats(a, b, name, rtol=1e-3, atol=1e-2):
     err = (a.float() - b.float()).abs()
@@ -122,3 +131,35 @@ def test_cuda_vae_on_reference_fixture():
     dec = ae.decode(fix["z_in"].cuda().half())
     mx, frac = _stats(dec.cpu(), fix["dec"], "vae decode", atol=2e-2)
     assert frac == 0.0
+
+
+@pytest.mark.gpu
+def test_cuda_video_decoder_on_reference_fixture():
+    """AutoencoderKLTemporal.decode(z, timesteps=T) -- VideoResBlocks ((3,1,1) time_stack, GroupNorm over
+    (T,H,W), blend weighing the temporal branch) and the AE3DConv output conv -- against the fixture produced by the
+    unmodified temporal_ae.VideoDecoder, and through DiffusionEngine.decode_first_stage's timesteps hook."""
+    from hi3d_official_b200.vae import AutoencoderKLTemporal, VideoDecoder
+    fix = _load("vae_video_ch64.pt")
+    cfg = spec.VAEConfig.from_ddconfig(fix["ddconfig"], 4)
+    sd_dec = spec.synth_state_dict(spec.video_decoder_param_shapes(cfg, (3, 1, 1)), seed=fix["seed"])
+    sd_2d = spec.synth_state_dict(spec.vae_param_shapes(cfg), seed=fix["seed"])
+    ae = AutoencoderKLTemporal(embed_dim=4, ddconfig=fix["ddconfig"], video_kernel_size=[3, 1, 1], time_mode="conv-only")
+    sd = {k: v for k, v in sd_2d.items() if not k.startswith("decoder.")}
+    sd.update(sd_dec)
+    # the fixture ran the bare VideoDecoder: make post_quant_conv the identity (1x1, 4 -> 4)
+    sd["post_quant_conv.weight"] = torch.eye(4).view(4, 4, 1, 1)
+    sd["post_quant_conv.bias"] = torch.zeros(4)
+    ae.load_state_dict(sd, strict=True)
+    ae = ae.cuda().half()
+    assert isinstance(ae.decoder, VideoDecoder)
+    T = fix["T"]
+    dec = ae.decode(fix["z"].cuda().half(), timesteps=T)
+    mx, frac = _stats(dec.cpu(), fix["dec"], f"video decoder (T={T}, 2 clips)", atol=2e-2)
+    assert frac == 0.0
+    # frames matter: a frame-reversed clip is not the frame-reversed output (temporal convs / (T,H,W) statistics are live)
+    dec_r = ae.decode(fix["z"].flip(0).cuda().half(), timesteps=T).flip(0)
+    assert float((dec_r.float() - dec.float()).abs().max()) > 1e-2
+    with pytest.raises(ValueError):
+        ae.decode(fix["z"].cuda().half())                       # the temporal decoder needs timesteps
+    with pytest.raises(NotImplementedError):
+        AutoencoderKLTemporal(embed_dim=4, ddconfig=fix["ddconfig"], video_kernel_size=3)

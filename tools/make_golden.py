@@ -31,8 +31,31 @@ def cond(T, cc, adm, hw, seed):
 
 
 @torch.no_grad()
+def video_decoder_fixture():
+    """the unmodified temporal_ae.VideoDecoder (time_mode 'conv-only', video_kernel_size [3, 1, 1]) run as
+    Decoder.forward(z, timesteps=T) on seeded synthetic weights, 2 clips x 4 frames, 16x16 latents."""
+    R.setup()
+    from sgm.modules.autoencoding.temporal_ae import VideoDecoder
+    dd = dict(VAE_DD, attn_type="vanilla")
+    cfg = spec.VAEConfig.from_ddconfig(VAE_DD, 4)
+    sd = spec.synth_state_dict(spec.video_decoder_param_shapes(cfg, (3, 1, 1)), seed=2)
+    ref = VideoDecoder(**dd, video_kernel_size=[3, 1, 1], time_mode="conv-only").eval()
+    ref.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()}, strict=True)
+    T = 4
+    g = torch.Generator().manual_seed(8)
+    z = torch.randn(2 * T, 4, 16, 16, generator=g)
+    out = ref(z, timesteps=T)
+    fix = dict(ddconfig=VAE_DD, seed=2, T=T, z=z, dec=out, video_kernel_size=[3, 1, 1])
+    torch.save(fix, os.path.join(OUT, "vae_video_ch64.pt"))
+    print("video decoder", tuple(out.shape), float(out.abs().mean()))
+
+
+@torch.no_grad()
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-video" in sys.argv:
+        video_decoder_fixture()
+        return
     torch.manual_seed(0)
     # ---- stage-1 style UNet (8 input channels), T=4, 16x16 latents: denoiser outputs at 3 sigmas + 3-step sampler
     for tag, kw, cc, adm, scale in (("s1", UNET_KW, 4, 768, 2.5), ("s2", UNET2_KW, 13, 512, 2.0)):
@@ -70,6 +93,7 @@ def main():
                dec=ae.decode(z_in))
     torch.save(fix, os.path.join(OUT, "vae_ch64.pt"))
     print("vae", float(fix["z_mode"].abs().mean()), float(fix["dec"].abs().mean()))
+    video_decoder_fixture()
 
 
 if __name__ == "__main__":
