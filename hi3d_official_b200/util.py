@@ -34,8 +34,16 @@ TARGET_ALIASES: Dict[str, str] = {
     "sgm.modules.autoencoding.temporal_ae.VideoDecoder": "hi3d_official_b200.vae.VideoDecoder",
     "sgm.modules.diffusionmodules.model.Encoder": "hi3d_official_b200.vae.Encoder",
     "sgm.modules.diffusionmodules.model.Decoder": "hi3d_official_b200.vae.Decoder",
-    "sgm.modules.GeneralConditioner": "hi3d_official_b200.engine.PassThroughConditioner",
-    "sgm.modules.encoders.modules.GeneralConditioner": "hi3d_official_b200.engine.PassThroughConditioner",
+    "sgm.modules.GeneralConditioner": "hi3d_official_b200.conditioner.GeneralConditioner",
+    "sgm.modules.encoders.modules.GeneralConditioner": "hi3d_official_b200.conditioner.GeneralConditioner",
+    "sgm.modules.encoders.modules.ConcatTimestepEmbedderND": "hi3d_official_b200.conditioner.ConcatTimestepEmbedderND",
+    "sgm.modules.encoders.modules.VideoPredictionEmbedderWithEncoder":
+        "hi3d_official_b200.conditioner.VideoPredictionEmbedderWithEncoder",
+    "sgm.modules.encoders.modules.FrozenOpenCLIPImagePredictionEmbedder":
+        "hi3d_official_b200.conditioner.FrozenOpenCLIPImagePredictionEmbedder",
+    "sgm.modules.encoders.modules.FrozenOpenCLIPImageEmbedder": "hi3d_official_b200.conditioner.FrozenOpenCLIPImageEmbedder",
+    "vtdm.encoders.DepthEmbedder": "hi3d_official_b200.conditioner.DepthEmbedder",
+    "vtdm.encoders.AesEmbedder": "hi3d_official_b200.conditioner.AesEmbedder",
     "vtdm.vtdm_gen_v01.VideoLDM": "hi3d_official_b200.engine.VideoLDM",
     "vtdm.vtdm_gen_stage2_degradeImage.VideoLDM": "hi3d_official_b200.engine.VideoLDMStage2",
     "sgm.models.diffusion.DiffusionEngine": "hi3d_official_b200.engine.DiffusionEngine",
