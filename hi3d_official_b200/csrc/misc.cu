@@ -76,6 +76,22 @@ __global__ void sampler_post_kernel(const __half* __restrict__ net, int net_ld, 
   }
 }
 
+// out = c0 x0 + c1 x1 + c2 x2 + c3 x3 with per-sample fp32 coefficients: the solver algebra of the multi-evaluation samplers
+// (Heun's trapezoid update, DPM-Solver++(2M)'s extrapolated update) on the fp32 sampler state, one launch.
+__global__ void lincomb4_kernel(float* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ x1,
+                                const float* __restrict__ x2, const float* __restrict__ x3, const float* __restrict__ c0,
+                                const float* __restrict__ c1, const float* __restrict__ c2, const float* __restrict__ c3,
+                                int per_sample, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int f = (int)(i / per_sample);
+  float v = c0[f] * x0[i];
+  if (x1) v += c1[f] * x1[i];
+  if (x2) v += c2[f] * x2[i];
+  if (x3) v += c3[f] * x3[i];
+  out[i] = v;
+}
+
 __global__ void renoise_blend_kernel(float* __restrict__ lat, const float* __restrict__ init, const float* __restrict__ z,
                                      float alpha, float sigma, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +233,19 @@ extern "C" int hi3d_sampler_post(const void* net, int net_ld, const float* x, co
   sampler_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)net, net_ld, x, sigma, sigma_next, scale, T, F, Cx, H * W, x_out, denoised_out);
   return check_launch("hi3d_sampler_post");
+}
+
+extern "C" int hi3d_sampler_lincomb4(float* out, const float* x0, const float* x1, const float* x2, const float* x3,
+                                     const float* c0, const float* c1, const float* c2, const float* c3, int F,
+                                     int64_t per_sample, void* stream) {
+  if (!out || !x0 || !c0 || F <= 0 || per_sample <= 0 || per_sample > 2147483647LL || (x1 && !c1) || (x2 && !c2) || (x3 && !c3)) {
+    set_error("hi3d_sampler_lincomb4: bad arguments");
+    return -2;
+  }
+  const long long n = (long long)F * per_sample;
+  lincomb4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, x0, x1, x2, x3, c0, c1, c2, c3,
+                                                                                (int)per_sample, n);
+  return check_launch("hi3d_sampler_lincomb4");
 }
 
 extern "C" int hi3d_renoise_blend(float* lat, const float* init, const float* z, float alpha, float sigma, int64_t n,

@@ -237,6 +237,23 @@ def sampler_post(net: torch.Tensor, x: torch.Tensor, sigma: torch.Tensor, sigma_
                                        x_out.data_ptr(), _ptr(denoised_out), _stream()), "hi3d_sampler_post")
 
 
+def sampler_lincomb(out: torch.Tensor, terms):
+    """out = sum_k c_k[f] * x_k; terms = [(x_k fp32 [F, ...], c_k fp32 [F]), ...] (1..4 terms)."""
+    if not 1 <= len(terms) <= 4:
+        raise ValueError("1..4 terms")
+    _chk32(out, "out")
+    F_ = out.shape[0]
+    xs, cs = [], []
+    for x, c in terms:
+        _chk32(x, "x"); _chk32(c, "c")
+        if x.shape != out.shape or c.numel() != F_:
+            raise ValueError("lincomb: shape mismatch")
+        xs.append(x.data_ptr()); cs.append(c.data_ptr())
+    xs += [None] * (4 - len(xs)); cs += [None] * (4 - len(cs))
+    N.check(N.load().hi3d_sampler_lincomb4(out.data_ptr(), *xs, *cs, F_, out.numel() // F_, _stream()), "hi3d_sampler_lincomb4")
+    return out
+
+
 def renoise_blend(lat: torch.Tensor, init: torch.Tensor, z: torch.Tensor, alpha: float, sigma: float):
     _chk32(lat, "lat"); _chk32(init, "init"); _chk32(z, "z")
     N.check(N.load().hi3d_renoise_blend(lat.data_ptr(), init.data_ptr(), z.data_ptr(), alpha, sigma, lat.numel(),

@@ -262,6 +262,21 @@ class _FusedState:
         plan.run()
         ops.sampler_post(plan.net_out.t, x, sigma, next_sigma, self.scale, x_out, den)
 
+    def denoise(self, x: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
+        """Guided denoised latents D(x, sigma) on the fused path (sampler_pre -> launch plan -> sampler_post): the network
+        evaluation of ANY sampler (Heun's second evaluation, DPM-Solver++), without the Euler update."""
+        plan = self.plan
+        x = x.contiguous()
+        sigma = sigma.contiguous()
+        F_, Cx, H, W = x.shape
+        ops.sampler_pre(x, sigma, self.cuc, self.cc, plan.xin.t.view(2 * F_, H, W, CIN_PAD), c_noise_out=plan.t_in)
+        plan.run()
+        den = torch.empty_like(x)
+        if getattr(self, "_scratch", None) is None or self._scratch.shape != x.shape:
+            self._scratch = torch.empty_like(x)
+        ops.sampler_post(plan.net_out.t, x, sigma, sigma, self.scale, self._scratch, den)
+        return den
+
     def step(self, x: torch.Tensor, sigma: torch.Tensor, next_sigma: torch.Tensor, want_denoised: bool = False):
         if self.use_graph and not want_denoised and x.shape == self._gx.shape:
             self._gx.copy_(x)
@@ -317,35 +332,18 @@ class BaseDiffusionSampler:
         return x, s_in, sigmas, num_sigmas, cond, uc
 
     def denoise(self, x, denoiser, sigma, cond, uc):
+        """sampling.py:54-57.  When `denoiser` is a fusable binding the guided D(x, sigma) comes from the fused kernels (one
+        network evaluation = sampler_pre -> launch plan -> sampler_post), whatever the solver around it is."""
+        st = self._fused_state(denoiser, x, cond, default(uc, cond), refresh=False)
+        if st is not None:
+            return st.denoise(x, sigma)
+        if isinstance(denoiser, FusedDenoiser) and denoiser.shard is not None:
+            raise NotImplementedError("frame-sharded sampling needs the fused path (LinearPredictionGuider + "
+                                      f"VScalingWithEDMcNoise, fp32 CUDA latents); got {type(self.guider).__name__}, x {x.dtype}")
         denoised = denoiser(*self.guider.prepare_inputs(x, sigma, cond, uc))
         return self.guider(denoised, sigma)
 
-    def get_sigma_gen(self, num_sigmas):
-        sigma_generator = range(num_sigmas - 1)
-        if self.verbose:
-            try:
-                from tqdm import tqdm
-                sigma_generator = tqdm(sigma_generator, total=num_sigmas,
-                                       desc=f"Sampling with {self.__class__.__name__} for {num_sigmas} steps")
-            except ImportError:
-                pass
-        return sigma_generator
-
-
-class SingleStepDiffusionSampler(BaseDiffusionSampler):
-    def sampler_step(self, sigma, next_sigma, denoiser, x, cond, uc, *args, **kwargs):
-        raise NotImplementedError
-
-    def euler_step(self, x, d, dt):
-        return x + dt * d
-
-
-class EDMSampler(SingleStepDiffusionSampler):
-    def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
-
-    # -- fused path -------------------------------------------------------------------------------------------
+    # -- fused path (shared by every sampler) -------------------------------------------------------------------
     def _fused_state(self, denoiser, x, cond, uc, refresh: bool) -> Optional[_FusedState]:
         if not (isinstance(denoiser, FusedDenoiser) and denoiser.fusable()
                 and isinstance(self.guider, LinearPredictionGuider) and x.is_cuda and x.dtype == torch.float32):
@@ -376,6 +374,32 @@ class EDMSampler(SingleStepDiffusionSampler):
             st.key = ck
         return st
 
+
+    def get_sigma_gen(self, num_sigmas):
+        sigma_generator = range(num_sigmas - 1)
+        if self.verbose:
+            try:
+                from tqdm import tqdm
+                sigma_generator = tqdm(sigma_generator, total=num_sigmas,
+                                       desc=f"Sampling with {self.__class__.__name__} for {num_sigmas} steps")
+            except ImportError:
+                pass
+        return sigma_generator
+
+
+class SingleStepDiffusionSampler(BaseDiffusionSampler):
+    def sampler_step(self, sigma, next_sigma, denoiser, x, cond, uc, *args, **kwargs):
+        raise NotImplementedError
+
+    def euler_step(self, x, d, dt):
+        return x + dt * d
+
+
+class EDMSampler(SingleStepDiffusionSampler):
+    def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
+
     def _gamma(self, sigmas, i, num_sigmas):
         if self.s_churn == 0.0:       # avoids the reference's per-step D2H sync (sampling.py:112,134)
             return 0.0
@@ -389,13 +413,6 @@ class EDMSampler(SingleStepDiffusionSampler):
             st = self._fused_state(denoiser, x, cond, default(uc, cond), _refresh)
             if st is not None and type(self).possible_correction_step is EDMSampler.possible_correction_step:
                 return st.step(x, sigma, next_sigma)
-        if isinstance(denoiser, FusedDenoiser) and denoiser.shard is not None:
-            # the generic path below would run VideoUNet.forward on this rank's frames as if they were a whole clip (no
-            # K/V, halo or GroupNorm exchange): silently wrong results or diverging ranks
-            raise NotImplementedError(
-                "frame-sharded sampling is only implemented on the fused Euler path (EulerEDMSampler + "
-                "LinearPredictionGuider + VScalingWithEDMcNoise, s_churn = 0, fp32 CUDA latents); got "
-                f"{type(self).__name__} / {type(self.guider).__name__}, gamma={gamma}, x {x.dtype} on {x.device}")
         sigma_hat = sigma * (gamma + 1.0)
         if gamma > 0:
             eps = torch.randn_like(x) * self.s_noise
@@ -403,6 +420,7 @@ class EDMSampler(SingleStepDiffusionSampler):
         denoised = self.denoise(x, denoiser, sigma_hat, cond, uc)
         d = (x - denoised) / append_dims(sigma_hat, x.ndim)            # to_d, sampling_utils.py:34
         dt = append_dims(next_sigma - sigma_hat, x.ndim)
+        self._heun_ctx = (next_sigma - sigma_hat).float().contiguous() if x.is_cuda else None
         euler_step = self.euler_step(x, d, dt)
         return self.possible_correction_step(euler_step, x, d, dt, next_sigma, denoiser, cond, uc)
 
@@ -426,9 +444,11 @@ class EulerEDMSampler(EDMSampler):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# the two other samplers of the sgm surface that Hi3D-style configs can name.  Host-side step
-# algebra only; every denoiser evaluation goes through `self.denoise`, i.e. through the same CUDA launch plan
-# (generic path) -- they take 2x / 1x network evaluations per step and are not fused with the Euler kernels.
+# the two other samplers of the sgm surface that Hi3D-style configs can name.  Every network evaluation goes
+# through `self.denoise`, i.e. the fused sampler_pre -> launch plan -> sampler_post kernels when the denoiser binding is fusable
+# (guider, Denoiser scalings and the OpenAIWrapper concat included); the solver algebra on the (F, 4, h, w) fp32 state is one
+# hi3d_sampler_lincomb4 launch per update on CUDA (plain tensor expressions on CPU, where they are checked against the
+# unmodified reference classes).
 # ------------------------------------------------------------------------------------------------------------
 class HeunEDMSampler(EDMSampler):
     """sampling.py:236-254.  Second order: the slope at (x, sigma_hat) is averaged with the slope at the Euler point
@@ -438,7 +458,16 @@ class HeunEDMSampler(EDMSampler):
         if float(next_sigma.sum()) < 1e-14:
             return euler_step
         sig_n = append_dims(next_sigma, x.ndim)
-        d_next = (euler_step - self.denoise(euler_step, denoiser, next_sigma, cond, uc)) / sig_n
+        den_next = self.denoise(euler_step, denoiser, next_sigma, cond, uc)
+        if x.is_cuda and x.dtype == torch.float32 and getattr(self, "_heun_ctx", None) is not None:
+            # x + dt/2 (d + d'),  d' = (x_e - D')/sigma':  one hi3d_sampler_lincomb4 launch over (x, d, x_e, D')
+            dtv = self._heun_ctx                                                  # dt per sample, fp32 [F]
+            h = 0.5 * dtv
+            one = torch.ones_like(dtv)
+            return ops.sampler_lincomb(torch.empty_like(x), [(x.contiguous(), one), (d.contiguous(), h),
+                                                             (euler_step.contiguous(), h / next_sigma),
+                                                             (den_next.contiguous(), -h / next_sigma)])
+        d_next = (euler_step - den_next) / sig_n
         heun = x + (d + d_next) / 2.0 * dt
         return torch.where(sig_n > 0.0, heun, euler_step)
 
@@ -461,10 +490,19 @@ class DPMPP2MSampler(BaseDiffusionSampler):
         h = t_next - t
         keep = append_dims(self._sigma(t_next) / self._sigma(t), x.ndim)     # sigma_next / sigma
         gain = append_dims((-h).expm1(), x.ndim)                             # exp(-h) - 1 <= 0
-        x_first = keep * x - gain * denoised
+        fused = x.is_cuda and x.dtype == torch.float32
         if old_denoised is None or float(next_sigma.sum()) < 1e-14:
-            return x_first, denoised
+            if fused:        # (sigma'/sigma) x - expm1(-h) D : one hi3d_sampler_lincomb4 launch
+                k1, g1 = (self._sigma(t_next) / self._sigma(t)).float().contiguous(), (-(-h).expm1()).float().contiguous()
+                return ops.sampler_lincomb(torch.empty_like(x), [(x.contiguous(), k1), (denoised.contiguous(), g1)]), denoised
+            return keep * x - gain * denoised, denoised
         r = (t - self._t(previous_sigma)) / h
+        if fused:            # (sigma'/sigma) x - expm1(-h) ((1 + 1/(2r)) D - 1/(2r) D_old)
+            k1, g1 = (self._sigma(t_next) / self._sigma(t)).float().contiguous(), (-(-h).expm1()).float()
+            return ops.sampler_lincomb(torch.empty_like(x), [(x.contiguous(), k1),
+                                                             (denoised.contiguous(), (g1 * (1 + 1 / (2 * r))).contiguous()),
+                                                             (old_denoised.contiguous(), (-g1 / (2 * r)).contiguous())]), denoised
+        x_first = keep * x - gain * denoised
         w_new, w_old = append_dims(1 + 1 / (2 * r), x.ndim), append_dims(1 / (2 * r), x.ndim)
         x_second = keep * x - gain * (w_new * denoised - w_old * old_denoised)
         return torch.where(append_dims(next_sigma, x.ndim) > 0.0, x_second, x_first), denoised

@@ -214,6 +214,14 @@ int hi3d_sampler_post(const void* net, int net_ld, const float* x, const float* 
                       const float* scale, int T, int F, int Cx, int H, int W, float* x_out, float* denoised_out,
                       void* stream);
 
+/* Solver algebra of the multi-evaluation samplers on the fp32 sampler state: out = sum_k c_k[f] * x_k, up to four
+ * terms (x1..x3 may be NULL), fp32 NCHW tensors of F samples x per_sample values, coefficients fp32 [F] on the device.
+ * HeunEDMSampler (sampling.py:236-254): x + dt/2 (d + d') with d = (x - D)/sigma, d' = (x_e - D')/sigma'
+ *   = (1 + dt/(2 sigma)) x - dt/(2 sigma) D + dt/(2 sigma') x_e - dt/(2 sigma') D'.
+ * DPMPP2MSampler (sampling.py:305-379): (sigma'/sigma) x - expm1(-h) ((1 + 1/(2r)) D - 1/(2r) D_old). */
+int hi3d_sampler_lincomb4(float* out, const float* x0, const float* x1, const float* x2, const float* x3, const float* c0,
+                          const float* c1, const float* c2, const float* c3, int F, int64_t per_sample, void* stream);
+
 /* Stage-2 re-noise blend (pipeline_i2v_eval_v02.py:131-132): lat = lat*(1-a) + (init*sigma + z)*a, fp32. */
 int hi3d_renoise_blend(float* lat, const float* init, const float* z, float alpha, float sigma, int64_t n,
                        void* stream);

@@ -324,3 +324,42 @@ def test_pack_geglu_padded_rows_are_zero():
     assert got_w.shape == (192, 64) and got_b.shape == (192,)
     assert torch.equal(got_w[:128, :32], pw) and not bool(got_w[128:].any()) and not bool(got_w[:, 32:].any())
     assert torch.equal(got_b[:128], pb) and not bool(got_b[128:].any())
+
+
+def test_fused_heun_and_dpmpp2m_match_generic_path():
+    """HeunEDMSampler / DPMPP2MSampler with a fusable denoiser binding (network evaluations through
+    sampler_pre -> launch plan -> sampler_post, solver algebra through hi3d_sampler_lincomb4) against the same samplers driven
+    by the reference-style closure (generic path: OpenAIWrapper / Denoiser / guider in tensor expressions)."""
+    from hi3d_official_b200 import configs, sampling, spec
+    T, h = 4, 16
+    model = configs.build_engine(1, device=DEV, unet_overrides=dict(model_channels=64), vae_overrides=dict(ch=64),
+                                 num_steps=3, num_frames=T)
+    spec.synth_fill_(model, seed=1, fast=False)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(T, 4, h, h, generator=g).to(DEV)
+    c = dict(crossattn=torch.randn(1, 1, 1024, generator=g).to(DEV), vector=torch.randn(1, 768, generator=g).to(DEV),
+             concat=(torch.randn(T, 4, h, h, generator=g) * 0.18).to(DEV))
+    uc = dict(crossattn=torch.zeros_like(c["crossattn"]), vector=c["vector"], concat=torch.zeros_like(c["concat"]))
+    kw = dict(num_steps=3, device=DEV,
+              discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization", "params": {"sigma_max": 700.0}},
+              guider_config={"target": "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
+                             "params": {"num_frames": T, "max_scale": 2.5, "min_scale": 1.0}})
+    fused = model.bind_denoiser(image_only_indicator=None, num_video_frames=T)
+
+    def closure(inp, sig, cc):
+        return model.denoiser(model.model, inp, sig, cc, image_only_indicator=None, num_video_frames=T)
+    for cls in (sampling.HeunEDMSampler, sampling.DPMPP2MSampler):
+        smp = cls(**kw)
+        n0 = N_launches()
+        a = smp(fused, x.clone(), cond=c, uc=uc)
+        used = N_launches() - n0
+        b = cls(**kw)(closure, x.clone(), cond=c, uc=uc)
+        err = float((a - b).abs().max())
+        print(f"[{cls.__name__}] fused vs generic max|err| {err:.3e} (mean|x| {float(b.abs().mean()):.3e}); {used} hi3d launches")
+        assert torch.isfinite(a).all() and err < 3e-2 * max(1.0, float(b.abs().max()))
+        assert smp._fused, "the fused state was never built"
+
+
+def N_launches():
+    from hi3d_official_b200 import _native
+    return _native.launch_count()
