@@ -606,4 +606,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:          # a failed rank must not leave its peers waiting in a collective until the NCCL timeout
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

@@ -310,6 +310,12 @@ class _Plan:
         self.gn_sums_local = torch.zeros(self.B, 32, 2, dtype=torch.float32, device=dev)
         self._cond_key = None
         self._compile()
+        if self.peer is not None:
+            # ranks build their plans (weight packing, tensor maps) at different speeds: meet on the host once, so that the
+            # first exchange kernel of the step does not spin for seconds on a rank that is still compiling
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier(group=self.peer.pg)
 
     # ---- helpers -----------------------------------------------------------------------------------------------
     def _gemm(self, lst, segs_fn, W, out: LazyBuf, M, **kw):
