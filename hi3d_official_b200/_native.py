@@ -36,7 +36,8 @@ class GemmParams(C.Structure):
                 ("rb_div", C.c_int32), ("rb_mod", C.c_int32), ("rb_ld", C.c_int32), ("act", C.c_int32),
                 ("residual", C.c_void_p), ("res_ld", C.c_int32),
                 ("blend_x", C.c_void_p), ("blend_ld", C.c_int32), ("alpha", C.c_float),
-                ("out", C.c_void_p), ("out_ld", C.c_int32)]
+                ("out", C.c_void_p), ("out_ld", C.c_int32),
+                ("gn_stats", C.c_void_p), ("gn_unit", C.c_int32), ("gn_rows", C.c_int32)]
 
 
 _lib = None
@@ -57,6 +58,12 @@ _SIGS = {
     "hi3d_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_void_p]),
+    "hi3d_groupnorm_apply_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int,
+                                             C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hi3d_groupnorm_unit_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "hi3d_groupnorm_group_sums": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p]),
     "hi3d_groupnorm_apply_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                             C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -123,7 +130,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.hi3d_abi_version() != 1:
+    if lib.hi3d_abi_version() != 2:
         raise Hi3dError("libhi3d_b200.so ABI version mismatch")
     _lib = lib
     return lib

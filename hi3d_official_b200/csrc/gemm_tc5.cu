@@ -66,6 +66,11 @@ struct T5Params {
   float alpha;
   __half* out;
   int out_ld;
+  // GroupNorm statistics of the output (hi3d_gemm_params::gn_stats): per-CTA shared table [gn_spt samples][gn_upt units][2],
+  // flushed with global atomics once per tile
+  float* gn_stats;
+  int gn_unit, gn_rows, gn_units, gn_nimg;   // channels per unit, GEMM-grid rows per image, units per image (N / unit), images
+  int gn_spt, gn_upt;                        // samples (images) a tile can touch, units an n-tile can touch
 };
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + MUFU error, far
@@ -173,6 +178,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       reinterpret_cast<volatile uint32_t*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 32);
   float* sbias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64);   // [2][256]
   uint8_t* scratch = smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048;                  // [EPI_WARPS][32 x 80]
+  float* gn_tab = reinterpret_cast<float*>(scratch + T5_EPI_WARPS * T5_SCR_BYTES);                  // [gn_spt][gn_upt][2]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role index
@@ -325,6 +331,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       const int nb = (unit0 % p.n_tiles) * BN + et;
       sbias[et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
     }
+    const bool gn_on = (p.gn_stats != nullptr) && !geglu;
+    const int gn_tab_n = gn_on ? p.gn_spt * p.gn_upt * 2 : 0;
+    for (int i = et; i < gn_tab_n; i += 32 * T5_EPI_WARPS) gn_tab[i] = 0.f;      // visible after the first bar.sync below
     for (int tile = unit0; tile < p.total_tiles; tile += nunits, at++) {
       const int mu = tile / p.n_tiles, nt = tile - mu * p.n_tiles;
       const int mt = mu * NCTA + (int)rank;
@@ -334,6 +343,21 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       long long mrow[4];                         // global rows of the rows this lane touches in the coalesced pattern
 #pragma unroll
       for (int i = 0; i < 4; i++) mrow[i] = t5_map(p, __shfl_sync(0xffffffffu, m, crow + 8 * i));
+      // GroupNorm statistics: image (sample) of this warp's rows relative to the first image the tile can touch
+      int gn_s0 = 0, gn_wsmp = -1, gn_srow[4] = {-1, -1, -1, -1};
+      bool gn_uniform = true;
+      if (gn_on) {
+        if (p.mode == HI3D_ROWS_CONV2D) gn_s0 = o.z0;
+        else if (p.mode == HI3D_ROWS_TEMPORAL) gn_s0 = o.z0 * p.Ho + o.y0;
+        else gn_s0 = (int)(((long long)mt * T5_BM) / p.gn_rows);
+        const int sl = (m >= 0) ? (int)(m / p.gn_rows) - gn_s0 : -1;
+        const int smax = __reduce_max_sync(0xffffffffu, sl);
+        const int smin = __reduce_min_sync(0xffffffffu, sl < 0 ? 0x7fffffff : sl);
+        gn_uniform = (smax < 0) || (smin == smax);
+        gn_wsmp = smax;                            // the warp's image when uniform (-1: no valid row)
+#pragma unroll
+        for (int i = 0; i < 4; i++) gn_srow[i] = __shfl_sync(0xffffffffu, sl, crow + 8 * i);
+      }
       const __half* rbp = nullptr;
       if (p.rowbias != nullptr && m >= 0) rbp = p.rowbias + (long long)((m / p.rb_div) % p.rb_mod) * p.rb_ld;
       const uint32_t buf = at & 1;
@@ -456,7 +480,87 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
             if (!(p.dbg & 1)) *reinterpret_cast<Half8*>(p.out + mrow[i] * p.out_ld + n + cchk * 8) = w8;
           }
           __syncwarp();
+          if (gn_on) {
+            // (sum, sumsq) of the values just stored (fp16-rounded: exactly what a statistics pass over the tensor sees).
+            // This lane: rows crow + 8 i, channels n + 8 cchk .. + 7.
+            const int u0 = n0 / p.gn_unit;                                  // first unit this n-tile can touch
+            if (gn_uniform) {
+              float s8[8], q8[8];
+#pragma unroll
+              for (int e = 0; e < 8; e++) s8[e] = q8[e] = 0.f;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                if (mrow[i] < 0 || !colok) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const float2 f = __half22float2(w8s[i].h[k]);
+                  s8[2 * k] += f.x; q8[2 * k] = fmaf(f.x, f.x, q8[2 * k]);
+                  s8[2 * k + 1] += f.y; q8[2 * k + 1] = fmaf(f.y, f.y, q8[2 * k + 1]);
+                }
+              }
+              // per-warp reduction over the 8 row groups through the (now idle) transpose scratch: [lane][16 floats]
+              float* sc = reinterpret_cast<float*>(scr);
+#pragma unroll
+              for (int e = 0; e < 8; e += 4) {
+                *reinterpret_cast<float4*>(sc + lane * 16 + e) = make_float4(s8[e], s8[e + 1], s8[e + 2], s8[e + 3]);
+                *reinterpret_cast<float4*>(sc + lane * 16 + 8 + e) = make_float4(q8[e], q8[e + 1], q8[e + 2], q8[e + 3]);
+              }
+              __syncwarp();
+              // lane j now owns channel n + j of the chunk
+              float S = 0.f, Q = 0.f;
+              const int jc = lane >> 3, je = lane & 7;
+#pragma unroll
+              for (int r8 = 0; r8 < 8; r8++) {
+                S += sc[(r8 * 4 + jc) * 16 + je];
+                Q += sc[(r8 * 4 + jc) * 16 + 8 + je];
+              }
+              const int smp = gn_wsmp;
+              if (smp >= 0 && smp < p.gn_spt && n + lane < p.N) {
+                const int u = (n + lane) / p.gn_unit - u0;
+                if (u >= 0 && u < p.gn_upt) {
+                  atomicAdd(&gn_tab[(smp * p.gn_upt + u) * 2], S);
+                  atomicAdd(&gn_tab[(smp * p.gn_upt + u) * 2 + 1], Q);
+                }
+              }
+              __syncwarp();
+            } else {
+              // rows of several images inside one warp (images smaller than 32 pixels): per-element shared atomics
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                if (mrow[i] < 0 || !colok || gn_srow[i] < 0 || gn_srow[i] >= p.gn_spt) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const float2 f = __half22float2(w8s[i].h[k]);
+                  const int c0 = n + cchk * 8 + 2 * k;
+                  const int ua = c0 / p.gn_unit - u0, ub = (c0 + 1) / p.gn_unit - u0;
+                  if (ua >= 0 && ua < p.gn_upt) {
+                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ua) * 2], f.x);
+                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ua) * 2 + 1], f.x * f.x);
+                  }
+                  if (ub >= 0 && ub < p.gn_upt) {
+                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ub) * 2], f.y);
+                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ub) * 2 + 1], f.y * f.y);
+                  }
+                }
+              }
+            }
+          }
         }
+      }
+      if (gn_on) {
+        // every epilogue warp has added its chunks of this tile: flush the table (one global atomic per touched entry)
+        asm volatile("bar.sync 2, %0;\n" ::"n"(32 * T5_EPI_WARPS) : "memory");
+        const int u0 = n0 / p.gn_unit;
+        for (int i = et; i < gn_tab_n; i += 32 * T5_EPI_WARPS) {
+          const float v = gn_tab[i];
+          if (v != 0.f) {
+            const int which = i & 1, ent = i >> 1;
+            const int smp = ent / p.gn_upt + gn_s0, u = ent % p.gn_upt + u0;
+            if (smp < p.gn_nimg && u < p.gn_units) atomicAdd(p.gn_stats + ((long long)smp * p.gn_units + u) * 2 + which, v);
+            gn_tab[i] = 0.f;
+          }
+        }
+        // (the bar.sync 1 at the top of the next tile orders these zeroing stores before the next tile's atomics)
       }
       sbias[(buf ^ 1) * 256 + et] = bnext;      // next tile's slice -> the buffer nobody reads until the next bar.sync
       // this warp is done reading the accumulator buffer
@@ -616,8 +720,24 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
       if (best < 0 || cost < best) { best = cost; BN = cand; }
     }
   }
+  // GroupNorm statistics in the epilogue: per-CTA table of (samples a tile can touch) x (units an n-tile can touch)
+  int gn_tab_bytes = 0;
+  if (p->gn_stats != nullptr) {
+    const int hw = (p->mode == HI3D_ROWS_PLAIN) ? p->gn_rows : p->Ho * p->Wo;
+    if (p->gn_unit <= 0 || (p->N % p->gn_unit) || p->gn_rows <= 0 || (p->M % p->gn_rows) || p->act == HI3D_ACT_GEGLU ||
+        (p->mode != HI3D_ROWS_PLAIN && p->gn_rows != hw)) {
+      set_error("hi3d_gemm_tc5: bad gn_stats arguments (unit %d, rows %d, N %d, M %d)", p->gn_unit, p->gn_rows, p->N, p->M);
+      return -2;
+    }
+    tp.gn_stats = p->gn_stats; tp.gn_unit = p->gn_unit; tp.gn_rows = p->gn_rows;
+    tp.gn_units = p->N / p->gn_unit; tp.gn_nimg = p->M / p->gn_rows;
+    tp.gn_spt = (p->mode == HI3D_ROWS_CONV2D) ? tp.tn : (p->mode == HI3D_ROWS_TEMPORAL) ? tp.th : (T5_BM / p->gn_rows + 2);
+    tp.gn_upt = BN / p->gn_unit + 2;
+    gn_tab_bytes = tp.gn_spt * tp.gn_upt * 2 * (int)sizeof(float);
+    if (gn_tab_bytes > 24 * 1024) return hi3d_gemm(p, stream);      // tiny images: the mma engine + a separate statistics pass
+  }
   const int stage_bytes = T5_A_BYTES + (BN / ncta) * 128;
-  int stages = T5_SMEM_BUDGET / stage_bytes;
+  int stages = (T5_SMEM_BUDGET - gn_tab_bytes) / stage_bytes;
   if (stages > T5_MAX_STAGES) stages = T5_MAX_STAGES;
   if (stages < 2) { return hi3d_gemm(p, stream); }
   tp.BN = BN; tp.stages = stages;
@@ -662,7 +782,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
   if (ensure_dyn_smem(gemm_tc5_kernel<1>, smem_total, attr_done1, "hi3d_gemm_tc5") ||
       ensure_dyn_smem(gemm_tc5_kernel<2>, smem_total, attr_done2, "hi3d_gemm_tc5")) return -1;
-  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
+  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + gn_tab_bytes + 1024;
   if (ncta == 2) {
     const int grid = 2 * (tp.total_tiles < units ? tp.total_tiles : units);
     cudaLaunchConfig_t cfg;

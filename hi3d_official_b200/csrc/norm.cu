@@ -116,10 +116,31 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
                 long long rows_per_cta, const float* __restrict__ fin, double count, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int apply_silu, __half* __restrict__ y,
                 long long y_sample_rows, long long y_row_off, __half* __restrict__ y_prev, __half* __restrict__ y_next,
-                long long frame_rows, int zero_lead, int zero_trail) {
+                long long frame_rows, int zero_lead, int zero_trail, const float* __restrict__ stats1,
+                const float* __restrict__ stats2, int unit, int ips) {
   __shared__ float smean[GN_GROUPS], srstd[GN_GROUPS];
+  __shared__ float ssum[GN_GROUPS * 2];
   const int C = C1 + C2, CV = C >> 3, cpg = C / GN_GROUPS;
   const int tid = threadIdx.x, n = blockIdx.y;
+  if (stats1 != nullptr) {
+    // statistics from the unit tables the producing GEMM epilogues accumulated (hi3d_gemm_params::gn_stats): group g of
+    // sample n = units [g cpg / unit, (g+1) cpg / unit) of the channel concat, over the `ips` images of the sample
+    if (tid < GN_GROUPS * 2) ssum[tid] = 0.f;
+    __syncthreads();
+    const int upg = cpg / unit, u1 = C1 / unit, u2 = C2 / unit;
+    const int items = GN_GROUPS * ips * upg;
+    for (int it = tid; it < items; it += blockDim.x) {
+      const int g = it / (ips * upg), rem = it - g * (ips * upg);
+      const int img = rem / upg, uu = rem - img * upg;
+      const int u = g * upg + uu;                                  // unit index within the concat
+      const long long im = (long long)n * ips + img;
+      const float* src = (u < u1) ? stats1 + (im * u1 + u) * 2 : stats2 + (im * u2 + (u - u1)) * 2;
+      atomicAdd(&ssum[2 * g], src[0]);
+      atomicAdd(&ssum[2 * g + 1], src[1]);
+    }
+    __syncthreads();
+    fin = ssum - (long long)n * (GN_GROUPS * 2);                   // so that the indexing below reads ssum[...]
+  }
   if (tid < GN_GROUPS) {      // `count` = elements per (sample, group) over ALL ranks
     const double mean = (double)fin[(long long)n * (GN_GROUPS * 2) + 2 * tid] / count;
     double var = (double)fin[(long long)n * (GN_GROUPS * 2) + 2 * tid + 1] / count - mean * mean;
@@ -405,6 +426,11 @@ extern "C" int hi3d_groupnorm_sums(const void* x1, int C1, const void* x2, int C
   return check_launch("hi3d_groupnorm_sums(finalize)");
 }
 
+// hi3d_groupnorm_apply_stats routes through the same launcher; its extra arguments travel in these thread-locals
+static thread_local const float* g_apply_stats1 = nullptr;
+static thread_local const float* g_apply_stats2 = nullptr;
+static thread_local int g_apply_unit = 0, g_apply_ips = 1;
+
 // y = [silu]((x - mean) * rstd * gamma + beta) with mean / rstd from `sums` over `count_rows` rows per sample
 // (count_rows = rows_per_sample for a single GPU, the GLOBAL row count when the sums were all-reduced over ranks).
 // Sample n of y starts at row n * y_sample_rows + y_row_off (haloed temporal buffers); 0, 0 -> dense like x.
@@ -431,7 +457,7 @@ extern "C" int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2,
               (long long)frame_rows, (long long)y_sample_rows, (long long)y_row_off);
     return -2;
   }
-  if (!sums || !gamma || !beta || !y || ((uintptr_t)y & 15) || count_rows <= 0) {
+  if ((!sums && !g_apply_stats1) || !gamma || !beta || !y || ((uintptr_t)y & 15) || count_rows <= 0) {
     set_error("hi3d_groupnorm_apply: bad arguments");
     return -2;
   }
@@ -453,8 +479,136 @@ extern "C" int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2,
       (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, sums,
       (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off,
       (__half*)y_prev_rank, (__half*)y_next_rank, frame_rows, (frame_rows > 0 && !y_prev_rank) ? 1 : 0,
-      (frame_rows > 0 && !y_next_rank) ? 1 : 0);
+      (frame_rows > 0 && !y_next_rank) ? 1 : 0, g_apply_stats1, g_apply_stats2, g_apply_unit, g_apply_ips);
   return check_launch("hi3d_groupnorm_apply");
+}
+
+// ---- unit statistics of an existing tensor: (sum, sumsq) per image and per `unit` consecutive channels, accumulated -------
+// grid (chunks, n_images); same streaming pattern as gn_stats_kernel, folding into units instead of the 32 groups.
+constexpr int GN_MAX_UNITS = 256;
+__global__ void __launch_bounds__(512)
+gn_unit_stats_kernel(const __half* __restrict__ x, int C, long long rows_per_image, long long rows_per_chunk, int unit,
+                     float* __restrict__ stats) {
+  __shared__ float su[GN_MAX_UNITS * 2];
+  const int CV = C >> 3, nu = C / unit;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < nu * 2; i += blockDim.x) su[i] = 0.f;
+  __syncthreads();
+  const int cv = tid % CV, rl = tid / CV, RL = blockDim.x / CV;
+  const int n = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows_per_image) r1 = rows_per_image;
+  const int c0 = cv * 8;
+  const __half* base = x + (long long)n * rows_per_image * C + c0;
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) s[e] = q[e] = 0.f;
+  for (long long r = r0 + rl; r < r1; r += RL) {
+    const Half8 v = ld_stream(base + r * C);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 f = __half22float2(v.h[k]);
+      s[2 * k] += f.x; q[2 * k] += f.x * f.x;
+      s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
+    }
+  }
+  int ucur = c0 / unit;
+  float as = 0.f, aq = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const int ui = (c0 + e) / unit;
+    if (ui != ucur) {
+      atomicAdd(&su[2 * ucur], as); atomicAdd(&su[2 * ucur + 1], aq);
+      as = aq = 0.f; ucur = ui;
+    }
+    as += s[e]; aq += q[e];
+  }
+  atomicAdd(&su[2 * ucur], as); atomicAdd(&su[2 * ucur + 1], aq);
+  __syncthreads();
+  for (int i = tid; i < nu * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * nu * 2 + i], su[i]);
+}
+
+// unit tables -> (sum, sumsq) per (sample, group): sums[n][32][2]
+__global__ void __launch_bounds__(256)
+gn_group_sums_kernel(const float* __restrict__ stats1, int C1, const float* __restrict__ stats2, int C2, int unit, int ips,
+                     float* __restrict__ sums) {
+  __shared__ float ssum[GN_GROUPS * 2];
+  const int tid = threadIdx.x, n = blockIdx.x;
+  if (tid < GN_GROUPS * 2) ssum[tid] = 0.f;
+  __syncthreads();
+  const int cpg = (C1 + C2) / GN_GROUPS, upg = cpg / unit, u1 = C1 / unit, u2 = C2 / unit;
+  const int items = GN_GROUPS * ips * upg;
+  for (int it = tid; it < items; it += blockDim.x) {
+    const int g = it / (ips * upg), rem = it - g * (ips * upg);
+    const int img = rem / upg, uu = rem - img * upg;
+    const int u = g * upg + uu;
+    const long long im = (long long)n * ips + img;
+    const float* src = (u < u1) ? stats1 + (im * u1 + u) * 2 : stats2 + (im * u2 + (u - u1)) * 2;
+    atomicAdd(&ssum[2 * g], src[0]);
+    atomicAdd(&ssum[2 * g + 1], src[1]);
+  }
+  __syncthreads();
+  if (tid < GN_GROUPS * 2) sums[(long long)n * (GN_GROUPS * 2) + tid] = ssum[tid];
+}
+
+static int unit_check(int C1, int C2, int unit, const char* who) {
+  const int C = C1 + C2;
+  if (unit <= 0 || (C % GN_GROUPS) || ((C / GN_GROUPS) % unit) || (C1 % unit) || (C2 % unit) || C1 / unit > GN_MAX_UNITS ||
+      C2 / unit > GN_MAX_UNITS) {
+    set_error("%s: unit %d must divide C1 = %d, C2 = %d and the channels per group %d (at most %d units per tensor)", who, unit,
+              C1, C2, C / GN_GROUPS, GN_MAX_UNITS);
+    return -2;
+  }
+  return 0;
+}
+
+extern "C" int hi3d_groupnorm_unit_stats(const void* x, int C, int n_images, int64_t rows_per_image, int unit, float* stats,
+                                         void* stream) {
+  if (!x || !stats || C <= 0 || (C % 8) || n_images <= 0 || n_images > 65535 || rows_per_image <= 0 || unit <= 0 ||
+      (C % unit) || C / unit > GN_MAX_UNITS || ((uintptr_t)x & 15)) {
+    set_error("hi3d_groupnorm_unit_stats: bad arguments (C=%d unit=%d n=%d rows=%lld)", C, unit, n_images, (long long)rows_per_image);
+    return -2;
+  }
+  const int CV = C / 8;
+  const int threads = (512 / CV) * CV;
+  const int RL = threads / CV;
+  long long chunks = (GN_TARGET_CTAS + n_images - 1) / n_images;
+  const long long max_by_rows = (rows_per_image + RL * GN_UNROLL - 1) / ((long long)RL * GN_UNROLL);
+  if (chunks > max_by_rows) chunks = max_by_rows;
+  if (chunks < 1) chunks = 1;
+  long long rpc = (rows_per_image + chunks - 1) / chunks;
+  rpc = (rpc + RL - 1) / RL * RL;
+  chunks = (rows_per_image + rpc - 1) / rpc;
+  gn_unit_stats_kernel<<<dim3((unsigned)chunks, n_images), threads, 0, (cudaStream_t)stream>>>((const __half*)x, C, rows_per_image,
+                                                                                              rpc, unit, stats);
+  return check_launch("hi3d_groupnorm_unit_stats");
+}
+
+extern "C" int hi3d_groupnorm_group_sums(const float* stats1, int C1, const float* stats2, int C2, int unit, int n_samples,
+                                         int imgs_per_sample, float* sums, void* stream) {
+  if (!stats2) C2 = 0;
+  if (!stats1 || !sums || n_samples <= 0 || imgs_per_sample <= 0) { set_error("hi3d_groupnorm_group_sums: bad arguments"); return -2; }
+  int rc = unit_check(C1, C2, unit, "hi3d_groupnorm_group_sums");
+  if (rc) return rc;
+  gn_group_sums_kernel<<<n_samples, 256, 0, (cudaStream_t)stream>>>(stats1, C1, stats2, C2, unit, imgs_per_sample, sums);
+  return check_launch("hi3d_groupnorm_group_sums");
+}
+
+extern "C" int hi3d_groupnorm_apply_stats(const void* x1, int C1, const float* stats1, const void* x2, int C2, const float* stats2,
+                                          int unit, int n_samples, int64_t rows_per_sample, int imgs_per_sample,
+                                          int64_t count_rows, const float* gamma, const float* beta, float eps, int apply_silu,
+                                          void* y, int64_t y_sample_rows, int64_t y_row_off, void* y_prev_rank, void* y_next_rank,
+                                          int64_t frame_rows, void* stream) {
+  if (!x2) { C2 = 0; stats2 = nullptr; }
+  if (!stats1 || (x2 && !stats2) || imgs_per_sample <= 0) { set_error("hi3d_groupnorm_apply_stats: null statistics table"); return -2; }
+  int rc = unit_check(C1, C2, unit, "hi3d_groupnorm_apply_stats");
+  if (rc) return rc;
+  g_apply_stats1 = stats1; g_apply_stats2 = stats2; g_apply_unit = unit; g_apply_ips = imgs_per_sample;
+  rc = hi3d_groupnorm_apply_halo(x1, C1, x2, C2, n_samples, rows_per_sample, nullptr, count_rows, gamma, beta, eps, apply_silu, y,
+                                 y_sample_rows, y_row_off, y_prev_rank, y_next_rank, frame_rows, stream);
+  g_apply_stats1 = g_apply_stats2 = nullptr; g_apply_unit = 0; g_apply_ips = 1;
+  return rc;
 }
 
 extern "C" int hi3d_groupnorm_silu(const void* x1, int C1, const void* x2, int C2, int n_samples,

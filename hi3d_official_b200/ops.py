@@ -71,7 +71,7 @@ class Gemm:
                  geom: Optional[dict] = None, bias: Optional[torch.Tensor] = None,
                  rowbias: Optional[torch.Tensor] = None, rb_div: int = 1, rb_mod: int = 1, act: int = ACT_NONE,
                  residual: Optional[torch.Tensor] = None, blend_x: Optional[torch.Tensor] = None, alpha: float = 0.0,
-                 engine: str = "mma"):
+                 engine: str = "mma", gn_stats: Optional[torch.Tensor] = None, gn_unit: int = 0, gn_rows: int = 0):
         _chk16(W, "W")
         _chk16(out, "out")
         Nn, K = W.shape
@@ -114,8 +114,13 @@ class Gemm:
         p.out, p.out_ld = out.data_ptr(), out.shape[-1]
         if out.shape[-1] < n_out or out.numel() < M * out.shape[-1] * (4 if p.out_up else 1):
             raise ValueError(f"out too small: {tuple(out.shape)} for M={M} N_out={n_out}")
+        if gn_stats is not None:      # GroupNorm statistics of the output from the epilogue (hi3d_gemm_params::gn_stats)
+            _chk32(gn_stats, "gn_stats")
+            if gn_unit <= 0 or Nn % gn_unit or gn_rows <= 0 or M % gn_rows or gn_stats.numel() < (M // gn_rows) * (Nn // gn_unit) * 2:
+                raise ValueError(f"gn_stats: unit {gn_unit} / rows {gn_rows} do not fit N={Nn}, M={M}, table {tuple(gn_stats.shape)}")
+            p.gn_stats, p.gn_unit, p.gn_rows = gn_stats.data_ptr(), gn_unit, gn_rows
         self.p = p
-        self._keep = (list(segs), W, out, bias, rowbias, residual, blend_x)   # keep storages alive
+        self._keep = (list(segs), W, out, bias, rowbias, residual, blend_x, gn_stats)   # keep storages alive
         self._fn = N.load().hi3d_gemm_tc5 if engine == "tc5" else N.load().hi3d_gemm
         self.flops = 2.0 * M * Nn * K
         self.out = out
@@ -165,6 +170,35 @@ def groupnorm_apply(x1: torch.Tensor, x2: Optional[torch.Tensor], n_samples: int
                                                sums.data_ptr(), count_rows, gamma.data_ptr(), beta.data_ptr(), eps, int(silu),
                                                y.data_ptr(), y_sample_rows, y_row_off, y_prev, y_next, frame_rows, _stream()),
             "hi3d_groupnorm_apply")
+
+
+def groupnorm_apply_stats(x1: torch.Tensor, stats1: torch.Tensor, x2: Optional[torch.Tensor], stats2: Optional[torch.Tensor],
+                          unit: int, n_samples: int, rows_per_sample: int, imgs_per_sample: int, count_rows: int,
+                          gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, y: torch.Tensor,
+                          y_sample_rows: int = 0, y_row_off: int = 0, y_prev: Optional[int] = None, y_next: Optional[int] = None,
+                          frame_rows: int = 0):
+    """GroupNorm(32)[+SiLU] in ONE launch: statistics from the unit tables written by the producing GEMM epilogues."""
+    _chk16(x1, "x1"); _chk16(y, "y"); _chk32(stats1, "stats1"); _chk32(gamma, "gamma"); _chk32(beta, "beta")
+    c2 = 0 if x2 is None else x2.shape[-1]
+    if x2 is not None:
+        _chk16(x2, "x2"); _chk32(stats2, "stats2")
+    N.check(N.load().hi3d_groupnorm_apply_stats(x1.data_ptr(), x1.shape[-1], stats1.data_ptr(), _ptr(x2), c2, _ptr(stats2), unit,
+                                                n_samples, rows_per_sample, imgs_per_sample, count_rows, gamma.data_ptr(),
+                                                beta.data_ptr(), eps, int(silu), y.data_ptr(), y_sample_rows, y_row_off, y_prev,
+                                                y_next, frame_rows, _stream()), "hi3d_groupnorm_apply_stats")
+
+
+def groupnorm_unit_stats(x: torch.Tensor, n_images: int, rows_per_image: int, unit: int, stats: torch.Tensor):
+    _chk16(x, "x"); _chk32(stats, "stats")
+    N.check(N.load().hi3d_groupnorm_unit_stats(x.data_ptr(), x.shape[-1], n_images, rows_per_image, unit, stats.data_ptr(),
+                                               _stream()), "hi3d_groupnorm_unit_stats")
+
+
+def groupnorm_group_sums(stats1: torch.Tensor, C1: int, stats2: Optional[torch.Tensor], C2: int, unit: int, n_samples: int,
+                         imgs_per_sample: int, sums: torch.Tensor):
+    _chk32(stats1, "stats1"); _chk32(sums, "sums")
+    N.check(N.load().hi3d_groupnorm_group_sums(stats1.data_ptr(), C1, _ptr(stats2), C2, unit, n_samples, imgs_per_sample,
+                                               sums.data_ptr(), _stream()), "hi3d_groupnorm_group_sums")
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, M: int,

@@ -97,6 +97,18 @@ class LazyBuf:
         return self.arena.get(self.tag, self.rows, self.cols)
 
 
+class StatsBuf:
+    """One GroupNorm statistics table fp32 [n_img, units, 2] inside the plan's statistics arena (zeroed once per forward)."""
+    __slots__ = ("plan", "off", "n_img", "units")
+
+    def __init__(self, plan, off, n_img, units):
+        self.plan, self.off, self.n_img, self.units = plan, off, n_img, units
+
+    @property
+    def t(self) -> torch.Tensor:
+        return self.plan.stats_arena[self.off:self.off + self.n_img * self.units * 2]
+
+
 class VideoUNet(nn.Module):
     def __init__(self, **kwargs):
         super().__init__()
@@ -284,6 +296,13 @@ class _Plan:
             from . import peer as _peer
             self.peer = _peer.get_group(self.rank, self.world, self.dev)
         self.arena = Arena(self.dev, self.peer, ("qkv", "att", "ghalo") if self.peer is not None else ())
+        # GroupNorm statistics from the producing GEMM epilogues (hi3d_gemm_params::gn_stats): every GroupNorm is ONE launch
+        # (apply); HI3D_GN_FUSED=0 keeps the separate statistics pass (stats + finalize + apply)
+        self.gn_unit = net.cfg.model_channels // 32
+        self.gn_fused = (os.environ.get("HI3D_GN_FUSED", "1") != "0" and net.cfg.model_channels % 32 == 0
+                         and net.cfg.model_channels * max(net.cfg.channel_mult) // self.gn_unit <= 256)
+        self._stats_floats = 0
+        self.stats_arena = None
         self.steps: List = []          # main per-step launch list (built lazily as (kind, builder) then baked)
         self._build: List = []         # deferred builders, run after the arena is materialised
         self._cond_build: List = []
@@ -323,11 +342,41 @@ class _Plan:
         def build():
             k2 = {}
             for k, v in kw.items():
-                k2[k] = v.t if isinstance(v, LazyBuf) else v
+                k2[k] = v.t if isinstance(v, (LazyBuf, StatsBuf)) else v
             g = ops.Gemm(segs_fn(), W, out.t if isinstance(out, LazyBuf) else out, M, engine=self.engine, **k2)
             self.flops += g.flops if lst is self._build else 0.0
             return g
         lst.append(build)
+
+    def _stats(self, n_img: int, C: int) -> Optional[StatsBuf]:
+        if not self.gn_fused:
+            return None
+        sb = StatsBuf(self, self._stats_floats, n_img, C // self.gn_unit)
+        self._stats_floats += n_img * (C // self.gn_unit) * 2
+        return sb
+
+    def _gnkw(self, stats: Optional[StatsBuf], rows_per_img: int) -> dict:
+        """Gemm kwargs that make its epilogue accumulate the GroupNorm statistics of its output into `stats`."""
+        return {} if stats is None else dict(gn_stats=stats, gn_unit=self.gn_unit, gn_rows=rows_per_img)
+
+    def _gn(self, lst, srcs, n_samples: int, rows_per_sample: int, ips: int, gb, eps: float, silu: bool, y: LazyBuf,
+            count_rows: Optional[int] = None, **halo):
+        """GroupNorm(32)[+SiLU] of the channel concat of srcs = [(LazyBuf, C, StatsBuf | None), ...] into y.
+        Fused statistics: one apply launch reading the producers' unit tables; otherwise stats + finalize + apply."""
+        gam, bet = gb
+        x1, c1, st1 = srcs[0]
+        x2, c2, st2 = srcs[1] if len(srcs) > 1 else (None, 0, None)
+        C = c1 + c2
+        M = n_samples * rows_per_sample
+        ws = self.gn_ws
+        if self.gn_fused and st1 is not None and (x2 is None or st2 is not None):
+            self._call(lst, lambda: ops.groupnorm_apply_stats(
+                x1.t, st1.t, x2.t if x2 else None, st2.t if x2 else None, self.gn_unit, n_samples, rows_per_sample, ips,
+                count_rows or rows_per_sample, gam, bet, eps, silu, y.t, **halo), kind="groupnorm", bytes=4.0 * M * C)
+        else:
+            assert not halo and count_rows is None
+            self._call(lst, lambda: ops.groupnorm_silu(x1.t, x2.t if x2 else None, n_samples, rows_per_sample, gam, bet, eps,
+                                                       silu, y.t, ws), kind="groupnorm", bytes=6.0 * M * C)
 
     def _call(self, lst, fn, **meta):
         """meta: kind / flops / bytes = algorithmic work of the launch (read by bench.py's breakdown)."""
@@ -358,9 +407,11 @@ class _Plan:
         self._gemm(cl, lambda: [ops.SegSpec(self.y_h)], P["label_emb.2"][0], self.label, N, bias=P["label_emb.2"][1])
 
         # ---------------- main body ----------------
+        if self.gn_fused:      # first launch of every forward: the statistics tables the epilogues accumulate into
+            self._call(bl, lambda: self.stats_arena.zero_(), kind="memset")
         self.xin = A.want("xin", N * H * W, CIN_PAD)
-        hs: List[Tuple[LazyBuf, int, int, int]] = []          # (buffer, C, h, w)
-        cur: Tuple[LazyBuf, int, int, int] = None
+        hs: List[tuple] = []          # (buffer, C, h, w, stats)
+        cur: tuple = None
         self._pp = 0
 
         def next_out(rows, C, persist_tag=None):
@@ -375,60 +426,54 @@ class _Plan:
                 last = li == len(blk) - 1
                 tag = f"hs{bi}" if last else None
                 if L.kind == "conv_in":
-                    out = next_out(N * h * w, L.cout, tag)
-                    self._conv(bl, [self.xin], P[L.name], out, h, w, h, w)
-                    cur = (out, L.cout, h, w)
+                    out, st = next_out(N * h * w, L.cout, tag), self._stats(N, L.cout)
+                    self._conv(bl, [self.xin], P[L.name], out, h, w, h, w, **self._gnkw(st, h * w))
                 elif L.kind == "res":
-                    out = next_out(N * h * w, L.cout, tag)
-                    self._resblock(L, [cur[0]], [cur[1]], out, h, w)
-                    cur = (out, L.cout, h, w)
+                    out, st = next_out(N * h * w, L.cout, tag), self._stats(N, L.cout)
+                    self._resblock(L, [cur], out, st, h, w)
                 elif L.kind == "attn":
-                    out = next_out(N * h * w, L.cout, tag)
-                    self._transformer(L, cur[0], out, h, w)
-                    cur = (out, L.cout, h, w)
+                    out, st = next_out(N * h * w, L.cout, tag), self._stats(N, L.cout)
+                    self._transformer(L, cur, out, st, h, w)
                 elif L.kind == "down":
-                    out = next_out(N * (h // 2) * (w // 2), L.cout, tag)
-                    self._conv(bl, [cur[0]], P[L.name], out, h // 2, w // 2, h, w, stride=2)
+                    out, st = next_out(N * (h // 2) * (w // 2), L.cout, tag), self._stats(N, L.cout)
+                    self._conv(bl, [cur[0]], P[L.name], out, h // 2, w // 2, h, w, stride=2, **self._gnkw(st, (h // 2) * (w // 2)))
                     h, w = h // 2, w // 2
-                    cur = (out, L.cout, h, w)
+                cur = (out, L.cout, h, w, st)
             hs.append(cur)
         for L in self.net.plan_desc.middle:
-            out = next_out(N * h * w, L.cout)
+            out, st = next_out(N * h * w, L.cout), self._stats(N, L.cout)
             if L.kind == "res":
-                self._resblock(L, [cur[0]], [cur[1]], out, h, w)
+                self._resblock(L, [cur], out, st, h, w)
             else:
-                self._transformer(L, cur[0], out, h, w)
-            cur = (out, L.cout, h, w)
+                self._transformer(L, cur, out, st, h, w)
+            cur = (out, L.cout, h, w, st)
         for blk in self.plan_desc_blocks("output"):
             skip = hs.pop()
             assert (skip[2], skip[3]) == (h, w)
-            srcs, cs = [cur[0], skip[0]], [cur[1], skip[1]]
+            srcs = [cur, skip]
             for L in blk:
                 if L.kind == "res":
-                    out = next_out(N * h * w, L.cout)
-                    self._resblock(L, srcs, cs, out, h, w)
-                    cur = (out, L.cout, h, w)
+                    out, st = next_out(N * h * w, L.cout), self._stats(N, L.cout)
+                    self._resblock(L, srcs, out, st, h, w)
                 elif L.kind == "attn":
-                    out = next_out(N * h * w, L.cout)
-                    self._transformer(L, cur[0], out, h, w)
-                    cur = (out, L.cout, h, w)
+                    out, st = next_out(N * h * w, L.cout), self._stats(N, L.cout)
+                    self._transformer(L, cur, out, st, h, w)
                 elif L.kind == "up":
-                    out = next_out(N * 4 * h * w, L.cout)
-                    self._upconv(bl, cur[0], P[L.name], out, h, w)
+                    out, st = next_out(N * 4 * h * w, L.cout), self._stats(N, L.cout)
+                    self._upconv(bl, cur[0], P[L.name], out, h, w, **self._gnkw(st, h * w))
                     h, w = 2 * h, 2 * w
-                    cur = (out, L.cout, h, w)
+                cur = (out, L.cout, h, w, st)
         # out: GN32 -> SiLU -> conv3x3 (video_model.py:436-440,500-501)
         M = N * h * w
         g = A.want("gn", M, cur[1])
-        gam, bet = P["out.gn"]
-        src = cur[0]
-        self._call(bl, lambda: ops.groupnorm_silu(src.t, None, N, h * w, gam, bet, 1e-5, True, g.t, self.gn_ws),
-                   kind="groupnorm", bytes=6.0 * M * cur[1])
+        self._gn(bl, [(cur[0], cur[1], cur[4])], N, h * w, 1, P["out.gn"], 1e-5, True, g)
         self.net_out = A.want("net_out", M, COUT_PAD)
         self._conv(bl, [g], P["out.conv"], self.net_out, h, w, h, w)
 
         # ---------------- materialise buffers, bake launches ----------------
         A.materialise()
+        if self.gn_fused:
+            self.stats_arena = torch.zeros(max(self._stats_floats, 2), dtype=torch.float32, device=self.dev)
         self.steps = [b() for b in self._build]
         self.cond_steps = [b() for b in self._cond_build]
         self._build = self._cond_build = None
@@ -443,7 +488,7 @@ class _Plan:
         self._gemm(lst, lambda: ops.conv_taps([s.t for s in srcs]), Wt, out, M, mode=ops.ROWS_CONV2D,
                    geom=dict(Ho=ho, Wo=wo, Hs=hs_, Ws=ws_, stride=stride, ups=ups), bias=b, **kw)
 
-    def _upconv(self, lst, src: LazyBuf, wb, out: LazyBuf, h, w, n_img=None):
+    def _upconv(self, lst, src: LazyBuf, wb, out: LazyBuf, h, w, n_img=None, **kw):
         """Upsample (nearest x2) + conv3x3 (openaimodel.py:154-156) as four parity-class 2x2 convs on the source
         grid with pre-summed taps (pack.pack_upconv_parity): no upsampled tensor, 4/9 of the FLOPs."""
         parity, b = wb
@@ -451,60 +496,59 @@ class _Plan:
         M = n_img * h * w
         for (py, px), (Wt, shifts) in parity.items():
             self._gemm(lst, lambda shifts=shifts: [ops.SegSpec(src.t, dy=sy, dx=sx) for sy, sx in shifts], Wt, out, M,
-                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=b)
+                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=b, **kw)
 
     def _emb_slice(self, q):
         off, n = self.P["emb_off"][q]
         return self.emb_all[:, off:off + n]
 
-    def _resblock(self, L: Layer, srcs: List[LazyBuf], cs: List[int], out: LazyBuf, h: int, w: int):
+    def _resblock(self, L: Layer, srcs: List[tuple], out: LazyBuf, out_stats, h: int, w: int):
         """VideoResBlock (video_model.py:62-81) = spatial ResBlock (openaimodel.py:328-354) + temporal ResBlock
-        (dims=3, kernel (3,1,1), GroupNorm over (C/32, T, H, W)) + AlphaBlender, as 4 GN launches + 4 GEMMs."""
+        (dims=3, kernel (3,1,1), GroupNorm over (C/32, T, H, W)) + AlphaBlender, as 4 GN launches + 4 GEMMs.
+        srcs = [(buffer, C, h, w, stats), ...] (two entries = the skip concat); every GEMM whose output feeds a GroupNorm
+        accumulates that GroupNorm's statistics in its epilogue (`out_stats` for the block output)."""
         P, A, bl, N, T, B = self.P, self.arena, self._build, self.N, self.T, self.B
         n = L.name
         HW = h * w
         M = N * HW
+        cs = [s_[1] for s_ in srcs]
         cin, cout = sum(cs), L.cout
-        x1 = srcs[0]
-        x2 = srcs[1] if len(srcs) > 1 else None
+        x1 = srcs[0][0]
+        x2 = srcs[1][0] if len(srcs) > 1 else None
         g_in = A.want("gn", M, cin)
         hbuf = A.want("h", M, cout)
         g_mid = A.want("gn", M, cout)
         xs = A.want("xs", M, cout)
-        ws = self.gn_ws
+        st_h1, st_xs, st_h2 = self._stats(N, cout), self._stats(N, cout), self._stats(N, cout)
         # -- spatial half
-        gam, bet = P[n + "gn1"]
-        self._call(bl, lambda: ops.groupnorm_silu(x1.t, x2.t if x2 else None, N, HW, gam, bet, 1e-5, True, g_in.t, ws),
-                   kind="groupnorm", bytes=6.0 * M * cin)
+        self._gn(bl, [(s_[0], s_[1], s_[4]) for s_ in srcs], N, HW, 1, P[n + "gn1"], 1e-5, True, g_in)
         emb1 = self._emb_slice(n)
         self._gemm(bl, lambda: ops.conv_taps([g_in.t]), P[n + "conv1"][0], hbuf, M, mode=ops.ROWS_CONV2D,
-                   geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv1"][1], rowbias=emb1, rb_div=HW, rb_mod=N)
-        gam2, bet2 = P[n + "gn2"]
-        self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, N, HW, gam2, bet2, 1e-5, True, g_mid.t, ws),
-                   kind="groupnorm", bytes=6.0 * M * cout)
+                   geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv1"][1], rowbias=emb1, rb_div=HW, rb_mod=N,
+                   **self._gnkw(st_h1, HW))
+        self._gn(bl, [(hbuf, cout, st_h1)], N, HW, 1, P[n + "gn2"], 1e-5, True, g_mid)
         if cin != cout:
-            self._gemm(bl, lambda: ops.conv_taps([g_mid.t]) + [ops.SegSpec(s.t) for s in srcs], P[n + "conv2"][0], xs, M,
-                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1])
+            self._gemm(bl, lambda: ops.conv_taps([g_mid.t]) + [ops.SegSpec(s_[0].t) for s_ in srcs], P[n + "conv2"][0], xs, M,
+                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1], **self._gnkw(st_xs, HW))
         else:
             assert x2 is None
             self._gemm(bl, lambda: ops.conv_taps([g_mid.t]), P[n + "conv2"][0], xs, M, mode=ops.ROWS_CONV2D,
-                       geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1], residual=x1)
+                       geom=dict(Ho=h, Wo=w, Hs=h, Ws=w), bias=P[n + "conv2"][1], residual=x1, **self._gnkw(st_xs, HW))
         # -- temporal half: statistics over (T, H, W) per clip, 3-tap conv along frames
         q = n + "time_stack."
         g3, b3 = P[q + "gn1"]
         g4, b4 = P[q + "gn2"]
         emb2 = self._emb_slice(q)
+        ws = self.gn_ws
         if self.shard is None:
-            self._call(bl, lambda: ops.groupnorm_silu(xs.t, None, B, T * HW, g3, b3, 1e-5, True, g_mid.t, ws),
-                       kind="groupnorm", bytes=6.0 * M * cout)
+            self._gn(bl, [(xs, cout, st_xs)], B, T * HW, T, (g3, b3), 1e-5, True, g_mid)
             geo = dict(Ho=HW, Wo=1, T=T)
             self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv1"][0], hbuf, M, mode=ops.ROWS_TEMPORAL, geom=geo,
-                       bias=P[q + "conv1"][1], rowbias=emb2, rb_div=HW, rb_mod=N)
-            self._call(bl, lambda: ops.groupnorm_silu(hbuf.t, None, B, T * HW, g4, b4, 1e-5, True, g_mid.t, ws),
-                       kind="groupnorm", bytes=6.0 * M * cout)
+                       bias=P[q + "conv1"][1], rowbias=emb2, rb_div=HW, rb_mod=N, **self._gnkw(st_h2, HW))
+            self._gn(bl, [(hbuf, cout, st_h2)], B, T * HW, T, (g4, b4), 1e-5, True, g_mid)
             # x_t = xs + conv(...);  out = alpha*xs + (1-alpha)*x_t   (util.py:358-369)
             self._gemm(bl, lambda: ops.temporal_taps(g_mid.t), P[q + "conv2"][0], out, M, mode=ops.ROWS_TEMPORAL, geom=geo,
-                       bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"])
+                       bias=P[q + "conv2"][1], residual=xs, blend_x=xs, alpha=P[n + "alpha"], **self._gnkw(out_stats, HW))
             return
         # frames sharded over ranks (SURVEY F9 / 8e): the (T,H,W) statistics need the (sum, sumsq) of every rank, the GN
         # output goes into a haloed [B, T+2, HW, C] buffer whose halo frames come from the neighbour ranks, and the 3-tap
@@ -512,16 +556,22 @@ class _Plan:
         gh = A.want("ghalo", B * (T + 2) * HW, cout)
         geo = dict(Ho=HW, Wo=1, T=T, Tin=T + 2, t_off=1)
         r, R = self.rank, self.world
-        for src, (gg, bb), wkey, dst, extra in (
-                (xs, (g3, b3), "conv1", hbuf, dict(rowbias=emb2, rb_div=HW, rb_mod=N)),
-                (hbuf, (g4, b4), "conv2", out, dict(residual=xs, blend_x=xs, alpha=P[n + "alpha"]))):
+        for src, sst, (gg, bb), wkey, dst, extra in (
+                (xs, st_xs, (g3, b3), "conv1", hbuf, dict(rowbias=emb2, rb_div=HW, rb_mod=N, **self._gnkw(st_h2, HW))),
+                (hbuf, st_h2, (g4, b4), "conv2", out, dict(residual=xs, blend_x=xs, alpha=P[n + "alpha"],
+                                                           **self._gnkw(out_stats, HW)))):
+            def local_sums(dst_sums, src=src, sst=sst):
+                """this rank's (sum, sumsq) per (clip, group): from the producer's unit table, or a statistics pass"""
+                if sst is not None:
+                    return ops.groupnorm_group_sums(sst.t, cout, None, 0, self.gn_unit, B, T, dst_sums)
+                return ops.groupnorm_sums(src.t, None, B, T * HW, dst_sums, ws)
             if self.peer is not None:
                 # peer memory: partial sums ride on the exchange kernel (all-reduce in one launch); the halo frames are
                 # stored into the neighbours' buffers by the apply kernel itself; a second exchange orders those stores
                 # before the conv (and, with the first, protects the single ghalo buffer from the next writer)
                 pg = self.peer
-                self._call(bl, lambda src=src: ops.groupnorm_sums(src.t, None, B, T * HW, self.gn_sums_local, ws),
-                           kind="groupnorm", bytes=2.0 * M * cout)
+                self._call(bl, lambda ls=local_sums: ls(self.gn_sums_local), kind="groupnorm",
+                           bytes=0.0 if sst is not None else 2.0 * M * cout)
                 self._call(bl, lambda: pg.exchange(self.gn_sums_local, self.gn_sums), kind="exchange")
 
                 def apply(src=src, gg=gg, bb=bb):
@@ -533,8 +583,8 @@ class _Plan:
                 self._call(bl, lambda: pg.exchange(), kind="exchange")
             else:
                 from . import dist as D
-                self._call(bl, lambda src=src: ops.groupnorm_sums(src.t, None, B, T * HW, self.gn_sums, ws), kind="groupnorm",
-                           bytes=2.0 * M * cout)
+                self._call(bl, lambda ls=local_sums: ls(self.gn_sums), kind="groupnorm",
+                           bytes=0.0 if sst is not None else 2.0 * M * cout)
                 self._call(bl, lambda: D.allreduce_sum_(self.gn_sums), kind="nccl")
                 self._call(bl, lambda src=src, gg=gg, bb=bb: ops.groupnorm_apply(
                     src.t, None, B, T * HW, self.gn_sums, self.Tg * HW, gg, bb, 1e-5, True, gh.t, (T + 2) * HW, HW),
@@ -543,9 +593,10 @@ class _Plan:
             self._gemm(bl, lambda: ops.temporal_taps(gh.t), P[q + wkey][0], dst, M, mode=ops.ROWS_TEMPORAL, geom=geo,
                        bias=P[q + wkey][1], **extra)
 
-    def _transformer(self, L: Layer, x: LazyBuf, out: LazyBuf, h: int, w: int):
+    def _transformer(self, L: Layer, xin: tuple, out: LazyBuf, out_stats, h: int, w: int):
         """SpatialVideoTransformer.forward (video_attention.py:230-301), see module docstring for the folds."""
         P, A, bl, cl, N, T, B = self.P, self.arena, self._build, self._cond_build, self.N, self.T, self.B
+        x = xin[0]
         n, C = L.name, L.cin
         HW = h * w
         M = N * HW
@@ -564,9 +615,7 @@ class _Plan:
         ops.Gemm([ops.SegSpec(tpe_in)], P[n + "tpe0"][0], tpe_h, T, bias=P[n + "tpe0"][1], act=ops.ACT_SILU)()
         ops.Gemm([ops.SegSpec(tpe_h)], P[n + "tpe2"][0], emb_t, T, bias=P[n + "tpe2"][1])()
 
-        gam, bet = P[n + "norm"]
-        self._call(bl, lambda: ops.groupnorm_silu(x.t, None, N, HW, gam, bet, 1e-6, False, gn.t, ws),
-                   kind="groupnorm", bytes=6.0 * M * C)
+        self._gn(bl, [(x, C, xin[4])], N, HW, 1, P[n + "norm"], 1e-6, False, gn)
         self._gemm(bl, lambda: [ops.SegSpec(gn.t)], P[n + "proj_in"][0], t0, M, bias=P[n + "proj_in"][1])
         tok = t0
         for d in range(self.net.cfg.transformer_depth):
@@ -632,7 +681,8 @@ class _Plan:
             self._gemm(bl, lambda: [ops.SegSpec(ffh.t)], P[qt + "ff2"][0], t0, M, bias=P[qt + "ff2"][1], residual=t1,
                        blend_x=t2, alpha=P[n + "alpha"])
             tok = t0
-        self._gemm(bl, lambda: [ops.SegSpec(tok.t)], P[n + "proj_out"][0], out, M, bias=P[n + "proj_out"][1], residual=x)
+        self._gemm(bl, lambda: [ops.SegSpec(tok.t)], P[n + "proj_out"][0], out, M, bias=P[n + "proj_out"][1], residual=x,
+                   **self._gnkw(out_stats, HW))
 
     def _ln(self, lst, x: LazyBuf, gb, y: LazyBuf, M, addvec=None, add_div=1, add_mod=1):
         g, b = gb

@@ -91,6 +91,16 @@ typedef struct {
   float alpha;
   void* out;                /* fp16 [M, out_ld]                                                        */
   int32_t out_ld;
+  /* GroupNorm statistics of the OUTPUT tensor, produced by the epilogue (the "GN-stats half" of the fused
+   * GroupNorm+SiLU+conv of openaimodel.py:257-261,292-305: the consumer of this tensor is a GroupNorm, whose separate
+   * statistics pass -- one full read of the tensor -- disappears).  gn_stats: fp32 [n_images, N / gn_unit, 2], (sum, sum of
+   * squares) of the stored fp16 values per image and per unit of gn_unit consecutive channels, ACCUMULATED with atomics (the
+   * caller zeroes it); image of a row = (row of the Ho x Wo / HW GEMM grid) / gn_rows.  Units, not the 32 groups, because a
+   * consumer may normalise the channel concat of two tensors (video_model.py:491) whose groups straddle the boundary;
+   * gn_unit divides every channels-per-group value of the network (model_channels / 32).  NULL = off. */
+  float* gn_stats;
+  int32_t gn_unit;
+  int32_t gn_rows;
 } hi3d_gemm_params;
 
 int hi3d_gemm(const hi3d_gemm_params* p, void* stream);
@@ -139,6 +149,22 @@ int hi3d_groupnorm_apply(const void* x1, int C1, const void* x2, int C2, int n_s
  * frames, mapped through hi3d_symm_open) and the last local frame into the leading slot of `y_next_rank`; NULL at the clip
  * boundaries: the local halo slot is then zero-filled (the Conv3d zero padding, openaimodel.py:252-261).  A hi3d_peer_exchange must
  * separate this launch from the conv that reads the halo slots. */
+/* The consumer side of hi3d_gemm_params::gn_stats: GroupNorm(32)[+SiLU] whose statistics come from the per-image, per-unit
+ * (sum, sumsq) tables written by the GEMM epilogues that produced x1 / x2 (stats1: fp32 [n_images, C1/unit, 2], stats2
+ * likewise or NULL) instead of a statistics pass over the tensor: ONE launch per GroupNorm.  Sample n spans images
+ * [n*imgs_per_sample, (n+1)*imgs_per_sample) -- 1 for the spatial GroupNorm32, T for the temporal ResBlock's reduction over
+ * (C/32, T, H, W) (video_model.py:71-76).  Other arguments as hi3d_groupnorm_apply_halo (frame_rows = 0: dense output). */
+int hi3d_groupnorm_apply_stats(const void* x1, int C1, const float* stats1, const void* x2, int C2, const float* stats2,
+                               int unit, int n_samples, int64_t rows_per_sample, int imgs_per_sample, int64_t count_rows,
+                               const float* gamma, const float* beta, float eps, int apply_silu, void* y, int64_t y_sample_rows,
+                               int64_t y_row_off, void* y_prev_rank, void* y_next_rank, int64_t frame_rows, void* stream);
+/* Unit statistics of an existing tensor (same table as hi3d_gemm_params::gn_stats, accumulated): for tensors not produced
+ * by an epilogue that can do it (the mma.sync engine uses this internally), and unit tables -> group sums
+ * fp32 [n_samples, 32, 2] (what the frame-sharded temporal GroupNorm all-reduces over ranks). */
+int hi3d_groupnorm_unit_stats(const void* x, int C, int n_images, int64_t rows_per_image, int unit, float* stats, void* stream);
+int hi3d_groupnorm_group_sums(const float* stats1, int C1, const float* stats2, int C2, int unit, int n_samples,
+                              int imgs_per_sample, float* sums, void* stream);
+
 int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2, int C2, int n_samples, int64_t rows_per_sample,
                               const float* sums, int64_t count_rows, const float* gamma, const float* beta, float eps,
                               int apply_silu, void* y, int64_t y_sample_rows, int64_t y_row_off, void* y_prev_rank,

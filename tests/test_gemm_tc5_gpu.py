@@ -149,3 +149,107 @@ def test_upsample_conv_as_parity_convs(engine, n, ci, co, hs):
                  geom=dict(Ho=hs, Wo=hs, Hs=hs, Ws=hs, out_up=1, out_py=py, out_px=px), bias=b, engine=engine)()
     # pre-summed fp16 taps add one more fp16 rounding of the weights: slightly wider tolerance
     close(out.view(n, 2 * hs, 2 * hs, co).permute(0, 3, 1, 2), ref, rtol=4e-3, name=f"upconv parity {engine}")
+
+
+# ---- GroupNorm statistics from the epilogue (hi3d_gemm_params::gn_stats) and the one-launch apply that consumes them ------
+def _unit_sums(out2d, n_img, rows, unit):
+    """(sum, sumsq) per image and per `unit` channels of the STORED fp16 tensor."""
+    o = out2d.float().view(n_img, rows, -1, unit)
+    return torch.stack([o.sum((1, 3)), (o * o).sum((1, 3))], -1)            # [n_img, units, 2]
+
+
+def _close_stats(got, ref, name):
+    err = (got - ref).abs()
+    tol = 2e-3 * ref.abs() + 2e-3 * ref.abs().mean()
+    assert bool((err <= tol).all()), f"{name}: max err {float(err.max()):.3e} (ref mean {float(ref.abs().mean()):.3e})"
+
+
+@pytest.mark.parametrize("engine", ["tc5", "mma"])
+@pytest.mark.parametrize("n,ci,co,hh,unit", [(4, 64, 320, 32, 10), (8, 64, 64, 8, 2), (32, 64, 64, 4, 2), (2, 128, 640, 16, 10)])
+def test_gemm_epilogue_gn_stats_conv(engine, n, ci, co, hh, unit):
+    x, w, b = rnd(n, ci, hh, hh), rnd(co, ci, 3, 3, scale=(9 * ci) ** -0.5), rnd(co, scale=0.1)
+    res = rnd(n * hh * hh, co, seed=9).to(H)
+    xh = nhwc(x)
+    M = n * hh * hh
+    out = torch.zeros(M, co, dtype=H, device=DEV)
+    stats = torch.zeros(n, co // unit, 2, device=DEV)
+    ops.Gemm(ops.conv_taps([xh]), pack.pack_conv2d(w), out, M, mode=ops.ROWS_CONV2D, geom=dict(Ho=hh, Wo=hh, Hs=hh, Ws=hh),
+             bias=b, residual=res, engine=engine, gn_stats=stats.view(-1), gn_unit=unit, gn_rows=hh * hh)()
+    ref = F.conv2d(xh.permute(0, 3, 1, 2).float(), w.to(H).float(), b, padding=1)
+    close(out.view(n, hh, hh, co).permute(0, 3, 1, 2), ref.to(H).float() + res.view(n, hh, hh, co).permute(0, 3, 1, 2).float(),
+          name="conv + residual (with stats)")
+    _close_stats(stats, _unit_sums(out, n, hh * hh, unit), f"epilogue stats conv {engine}")
+    # accumulate semantics: a second launch adds
+    ops.Gemm(ops.conv_taps([xh]), pack.pack_conv2d(w), out, M, mode=ops.ROWS_CONV2D, geom=dict(Ho=hh, Wo=hh, Hs=hh, Ws=hh),
+             bias=b, residual=res, engine=engine, gn_stats=stats.view(-1), gn_unit=unit, gn_rows=hh * hh)()
+    _close_stats(stats, 2 * _unit_sums(out, n, hh * hh, unit), f"epilogue stats accumulate {engine}")
+
+
+@pytest.mark.parametrize("pair", [-1, 1])
+def test_gemm_epilogue_gn_stats_temporal_plain_upconv(pair):
+    lib = __import__("hi3d_official_b200._native", fromlist=["x"]).load()
+    lib.hi3d_gemm_tc5_set_pair_mode(pair)
+    try:
+        # temporal taps, T = 8, 64 px frames (two frames per tile) and 256 px frames
+        for hw in (64, 256):
+            b_, c, co, T, unit = 2, 64, 320, 8, 10
+            M = b_ * T * hw
+            xh = rnd(M, c, seed=3).to(H)
+            w = rnd(co, c, 3, 1, 1, scale=(3 * c) ** -0.5)
+            out = torch.zeros(M, co, dtype=H, device=DEV)
+            stats = torch.zeros(b_ * T, co // unit, 2, device=DEV)
+            ops.Gemm(ops.temporal_taps(xh), pack.pack_conv3d_t(w), out, M, mode=ops.ROWS_TEMPORAL, geom=dict(Ho=hw, Wo=1, T=T),
+                     engine="tc5", gn_stats=stats.view(-1), gn_unit=unit, gn_rows=hw)()
+            _close_stats(stats, _unit_sums(out, b_ * T, hw, unit), f"epilogue stats temporal hw={hw}")
+        # plain rows (proj_out-like), ragged last tile, images of 100 rows
+        M, K, N, rows, unit = 700, 320, 320, 100, 10
+        a, w = rnd(M, K).to(H), rnd(N, K, scale=K ** -0.5).to(H)
+        out = torch.zeros(M, N, dtype=H, device=DEV)
+        stats = torch.zeros(M // rows, N // unit, 2, device=DEV)
+        ops.Gemm([ops.SegSpec(a)], w, out, M, engine="tc5", gn_stats=stats.view(-1), gn_unit=unit, gn_rows=rows)()
+        _close_stats(stats, _unit_sums(out, M // rows, rows, unit), "epilogue stats plain")
+        # nearest x2 + conv as four parity launches accumulating into one table
+        n, ci, co, hs, unit = 2, 64, 64, 16, 2
+        x, w = rnd(n, ci, hs, hs), rnd(co, ci, 3, 3, scale=(9 * ci) ** -0.5)
+        xh = nhwc(x)
+        out = torch.zeros(n * 4 * hs * hs, co, dtype=H, device=DEV)
+        stats = torch.zeros(n, co // unit, 2, device=DEV)
+        for (py, px), (Wt, shifts) in pack.pack_upconv_parity(w).items():
+            ops.Gemm([ops.SegSpec(xh, dy=sy, dx=sx) for sy, sx in shifts], Wt, out, n * hs * hs, mode=ops.ROWS_CONV2D,
+                     geom=dict(Ho=hs, Wo=hs, Hs=hs, Ws=hs, out_up=1, out_py=py, out_px=px), engine="tc5",
+                     gn_stats=stats.view(-1), gn_unit=unit, gn_rows=hs * hs)()
+        _close_stats(stats, _unit_sums(out, n, 4 * hs * hs, unit), "epilogue stats upconv")
+    finally:
+        lib.hi3d_gemm_tc5_set_pair_mode(-1)
+
+
+@pytest.mark.parametrize("silu,eps", [(True, 1e-5), (False, 1e-6)])
+def test_groupnorm_apply_from_unit_stats(silu, eps):
+    """hi3d_groupnorm_apply_stats: spatial (per image), temporal (T images per sample) and the two-source concat whose groups
+    straddle the source boundary (C1 = 1280 / 128, C2 = 640 / 64 -> 60 / 6 channels per group), against F.group_norm."""
+    for (n, rows, c1, c2, unit, ips) in ((4, 256, 320, 0, 10, 1), (4, 64, 128, 64, 2, 1), (8, 64, 64, 0, 2, 4), (2, 128, 1280, 640, 10, 1)):
+        C = c1 + c2
+        x1 = rnd(n * rows, c1, seed=1).to(H) * 1.5 + 0.3
+        x2 = (rnd(n * rows, c2, seed=2).to(H) * 0.7 - 0.2) if c2 else None
+        s1 = torch.zeros(n, c1 // unit, 2, device=DEV)
+        ops.groupnorm_unit_stats(x1, n, rows, unit, s1.view(-1))
+        _close_stats(s1, _unit_sums(x1, n, rows, unit), "unit stats")
+        s2 = None
+        if c2:
+            s2 = torch.zeros(n, c2 // unit, 2, device=DEV)
+            ops.groupnorm_unit_stats(x2, n, rows, unit, s2.view(-1))
+        gam, bet = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
+        y = torch.zeros(n * rows, C, dtype=H, device=DEV)
+        ns = n // ips
+        ops.groupnorm_apply_stats(x1, s1.view(-1), x2, None if s2 is None else s2.view(-1), unit, ns, rows * ips, ips, rows * ips,
+                                  gam, bet, eps, silu, y)
+        xc = x1 if x2 is None else torch.cat([x1, x2], 1)
+        ref = F.group_norm(xc.view(ns, rows * ips, C).permute(0, 2, 1).float(), 32, gam, bet, eps)
+        if silu:
+            ref = F.silu(ref)
+        close(y.view(ns, rows * ips, C).permute(0, 2, 1), ref, name=f"apply from stats n={n} C={c1}+{c2} ips={ips}")
+        if ips > 1 or c2 == 0:
+            sums = torch.zeros(ns, 32, 2, device=DEV)
+            ops.groupnorm_group_sums(s1.view(-1), c1, None, 0, unit, ns, ips, sums)
+            g = xc.float().view(ns, rows * ips, 32, C // 32)
+            _close_stats(sums, torch.stack([g.sum((1, 3)), (g * g).sum((1, 3))], -1), "group sums")
