@@ -485,26 +485,25 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
             // This lane: rows crow + 8 i, channels n + 8 cchk .. + 7.
             const int u0 = n0 / p.gn_unit;                                  // first unit this n-tile can touch
             if (gn_uniform) {
-              float s8[8], q8[8];
+              float2 s2[4], q2[4];                 // packed fp32 pairs: (sum, sumsq) of channels (2k, 2k+1) over this lane's rows
 #pragma unroll
-              for (int e = 0; e < 8; e++) s8[e] = q8[e] = 0.f;
+              for (int k = 0; k < 4; k++) s2[k] = q2[k] = make_float2(0.f, 0.f);
 #pragma unroll
               for (int i = 0; i < 4; i++) {
                 if (mrow[i] < 0 || !colok) continue;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   const float2 f = __half22float2(w8s[i].h[k]);
-                  s8[2 * k] += f.x; q8[2 * k] = fmaf(f.x, f.x, q8[2 * k]);
-                  s8[2 * k + 1] += f.y; q8[2 * k + 1] = fmaf(f.y, f.y, q8[2 * k + 1]);
+                  s2[k] = __fadd2_rn(s2[k], f);
+                  q2[k] = __ffma2_rn(f, f, q2[k]);
                 }
               }
               // per-warp reduction over the 8 row groups through the (now idle) transpose scratch: [lane][16 floats]
               float* sc = reinterpret_cast<float*>(scr);
-#pragma unroll
-              for (int e = 0; e < 8; e += 4) {
-                *reinterpret_cast<float4*>(sc + lane * 16 + e) = make_float4(s8[e], s8[e + 1], s8[e + 2], s8[e + 3]);
-                *reinterpret_cast<float4*>(sc + lane * 16 + 8 + e) = make_float4(q8[e], q8[e + 1], q8[e + 2], q8[e + 3]);
-              }
+              *reinterpret_cast<float4*>(sc + lane * 16) = make_float4(s2[0].x, s2[0].y, s2[1].x, s2[1].y);
+              *reinterpret_cast<float4*>(sc + lane * 16 + 4) = make_float4(s2[2].x, s2[2].y, s2[3].x, s2[3].y);
+              *reinterpret_cast<float4*>(sc + lane * 16 + 8) = make_float4(q2[0].x, q2[0].y, q2[1].x, q2[1].y);
+              *reinterpret_cast<float4*>(sc + lane * 16 + 12) = make_float4(q2[2].x, q2[2].y, q2[3].x, q2[3].y);
               __syncwarp();
               // lane j now owns channel n + j of the chunk
               float S = 0.f, Q = 0.f;
@@ -514,9 +513,21 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
                 S += sc[(r8 * 4 + jc) * 16 + je];
                 Q += sc[(r8 * 4 + jc) * 16 + 8 + je];
               }
+              // Segmented sum over the lanes of one unit (consecutive channels), so that ONE lane per unit touches the table:
+              // shared-memory float atomics are compare-and-swap loops, and ten lanes hammering one address made the first
+              // version of this block cost more than the statistics pass it replaces.
+              const int uabs = (n + lane < p.N) ? (n + lane) / p.gn_unit : -1 - lane;     // distinct negatives: never merged
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const float so = __shfl_up_sync(0xffffffffu, S, off), qo = __shfl_up_sync(0xffffffffu, Q, off);
+                const int uo = __shfl_up_sync(0xffffffffu, uabs, off);
+                if (lane >= off && uo == uabs) { S += so; Q += qo; }
+              }
+              const int unext = __shfl_down_sync(0xffffffffu, uabs, 1);
+              const bool seg_last = (lane == 31) || (unext != uabs);
               const int smp = gn_wsmp;
-              if (smp >= 0 && smp < p.gn_spt && n + lane < p.N) {
-                const int u = (n + lane) / p.gn_unit - u0;
+              if (seg_last && uabs >= 0 && smp >= 0 && smp < p.gn_spt) {
+                const int u = uabs - u0;
                 if (u >= 0 && u < p.gn_upt) {
                   atomicAdd(&gn_tab[(smp * p.gn_upt + u) * 2], S);
                   atomicAdd(&gn_tab[(smp * p.gn_upt + u) * 2 + 1], Q);

@@ -111,7 +111,9 @@ gn_finalize_kernel(const float* __restrict__ ws, int nchunks, float* __restrict_
 
 // ---- pass 2: y = [silu]((x - mean) * rstd * gamma + beta) ------------------------------------------
 // grid (row_slabs, n_samples), blockDim = RL * CV.
-__global__ void __launch_bounds__(512, 2)
+template <bool HALO>      // HALO = haloed output with peer stores / boundary zero fill (frame-sharded temporal GroupNorm only):
+                          // a template so that the dense kernel keeps its 64 registers (2 CTAs per SM)
+__global__ void __launch_bounds__(512)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, long long rows_per_sample,
                 long long rows_per_cta, const float* __restrict__ fin, double count, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int apply_silu, __half* __restrict__ y,
@@ -167,44 +169,18 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > rows_per_sample) r1 = rows_per_sample;
-  // SiLU with 1.25 MUFU operations per element instead of 2: the kernel was bound by the MUFU pipe (ncu: XU 56 % busy,
-  // DRAM 53 %), not by HBM.  Four sigmoids share ONE reciprocal: with a_i = 1 + 2^(-y_i log2 e), 1/a_0 = a_1 a_2 a_3 /
-  // (a_0 a_1 a_2 a_3) etc.  y is clamped at -20 for the exponential only (a_i <= 4.9e8, the product of four stays below
-  // FLT_MAX; silu(-20) = -4e-8 is below the fp16 subnormal step anyway), so the products cannot overflow.
+  // (A variant with one shared reciprocal per four sigmoids -- 1.25 MUFU operations per element instead of 2 -- was measured
+  // SLOWER: 128 us vs 76 us per launch in the ncu launch list of profiles/r02_*: the kernel is latency-bound at ~50 % issue /
+  // MUFU / DRAM utilisation, and the extra multiplies plus the register squeeze cost more than the MUFU slots they free.)
   auto xform = [&](Half8 v) {
-    float yv[8];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      const float2 f = __half22float2(v.h[k]);
-      yv[2 * k] = fmaf(f.x, A[2 * k], B[2 * k]);
-      yv[2 * k + 1] = fmaf(f.y, A[2 * k + 1], B[2 * k + 1]);
+      float2 f = __half22float2(v.h[k]);
+      f.x = f.x * A[2 * k] + B[2 * k];
+      f.y = f.y * A[2 * k + 1] + B[2 * k + 1];
+      if (apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+      v.h[k] = __floats2half2_rn(f.x, f.y);
     }
-    if (apply_silu) {
-      float a[8];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const float z0 = fminf(yv[2 * k] * -1.4426950408889634f, 28.853900817779268f);       // 20 * log2(e)
-        const float z1 = fminf(yv[2 * k + 1] * -1.4426950408889634f, 28.853900817779268f);
-        float e0, e1;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
-        a[2 * k] = 1.0f + e0;
-        a[2 * k + 1] = 1.0f + e1;
-      }
-#pragma unroll
-      for (int g4 = 0; g4 < 8; g4 += 4) {
-        const float p01 = a[g4] * a[g4 + 1], p23 = a[g4 + 2] * a[g4 + 3];
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
-        const float r01 = r * p23, r23 = r * p01;                 // 1 / (a0 a1), 1 / (a2 a3)
-        yv[g4] *= r01 * a[g4 + 1];
-        yv[g4 + 1] *= r01 * a[g4];
-        yv[g4 + 2] *= r23 * a[g4 + 3];
-        yv[g4 + 3] *= r23 * a[g4 + 2];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) v.h[k] = __floats2half2_rn(yv[2 * k], yv[2 * k + 1]);
     return v;
   };
   // Frame-sharded temporal GroupNorm: y is a haloed [n, T_local + 2, frame_rows, C] buffer.  The first local
@@ -212,17 +188,18 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   // halo slot of the next rank's (peer stores over NVLink): the one-frame halo exchange of the (3,1,1) conv rides on this
   // kernel's stores.  y_prev / y_next are the peers' buffer bases (NULL at the clip boundary: that slot stays zero = padding).
   const long long last0 = rows_per_sample - frame_rows;
-  __half* yp = y_prev ? y_prev + ((long long)n * y_sample_rows + (y_sample_rows - frame_rows)) * C + c0 : nullptr;
-  __half* yn = y_next ? y_next + ((long long)n * y_sample_rows - last0) * C + c0 : nullptr;
+  __half* yp = (HALO && y_prev) ? y_prev + ((long long)n * y_sample_rows + (y_sample_rows - frame_rows)) * C + c0 : nullptr;
+  __half* yn = (HALO && y_next) ? y_next + ((long long)n * y_sample_rows - last0) * C + c0 : nullptr;
   // At a clip boundary (no previous / next rank) the halo slot of THIS rank is the Conv3d zero padding: the buffer is
   // shared by layers of different geometry, so it is re-zeroed here by the threads that own the matching boundary frame.
-  __half* zl = zero_lead ? y + ((long long)n * y_sample_rows) * C + c0 : nullptr;                               // slot 0
-  __half* zt = zero_trail ? y + ((long long)n * y_sample_rows + (y_sample_rows - frame_rows) - last0) * C + c0 : nullptr;
+  __half* zl = (HALO && zero_lead) ? y + ((long long)n * y_sample_rows) * C + c0 : nullptr;                     // slot 0
+  __half* zt = (HALO && zero_trail) ? y + ((long long)n * y_sample_rows + (y_sample_rows - frame_rows) - last0) * C + c0 : nullptr;
   Half8 zero8;
   zero8.u = make_uint4(0u, 0u, 0u, 0u);
   bool remote = false;
   auto put = [&](long long rr, const Half8& o) {
     *reinterpret_cast<Half8*>(yb + rr * C) = o;
+    if (!HALO) return;
     if (rr < frame_rows) {
       if (yp != nullptr) { *reinterpret_cast<Half8*>(yp + rr * C) = o; remote = true; }
       if (zl != nullptr) *reinterpret_cast<Half8*>(zl + rr * C) = zero8;
@@ -475,11 +452,17 @@ extern "C" int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2,
   rows_per_cta = (rows_per_cta + RL - 1) / RL * RL;
   slabs = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
   if (slabs > 2147483647LL) { set_error("hi3d_groupnorm_apply: too many slabs"); return -2; }
-  gn_apply_kernel<<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
-      (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, sums,
-      (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off,
-      (__half*)y_prev_rank, (__half*)y_next_rank, frame_rows, (frame_rows > 0 && !y_prev_rank) ? 1 : 0,
-      (frame_rows > 0 && !y_next_rank) ? 1 : 0, g_apply_stats1, g_apply_stats2, g_apply_unit, g_apply_ips);
+  if (frame_rows > 0)
+    gn_apply_kernel<true><<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
+        (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, sums,
+        (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off,
+        (__half*)y_prev_rank, (__half*)y_next_rank, frame_rows, !y_prev_rank ? 1 : 0, !y_next_rank ? 1 : 0, g_apply_stats1,
+        g_apply_stats2, g_apply_unit, g_apply_ips);
+  else
+    gn_apply_kernel<false><<<dim3((unsigned)slabs, n_samples), threads, 0, st>>>(
+        (const __half*)x1, C1, (const __half*)x2, C2, rows_per_sample, rows_per_cta, sums,
+        (double)count_rows * (double)(C / GN_GROUPS), eps, gamma, beta, apply_silu, (__half*)y, y_sample_rows, y_row_off,
+        nullptr, nullptr, 0, 0, 0, g_apply_stats1, g_apply_stats2, g_apply_unit, g_apply_ips);
   return check_launch("hi3d_groupnorm_apply");
 }
 

@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from . import ops, pack
 from .spec import VAEConfig, vae_param_shapes
-from .unet import Arena, LazyBuf, _ParamTree
+from .unet import Arena, LazyBuf, StatsBuf, _ParamTree
 
 F16 = torch.float16
 CIN_PAD = 64
@@ -38,6 +38,15 @@ class _VAEPlan:
         self.flops = 0.0
         self.gn_ws = ops.groupnorm_ws(n, self.dev)
         self._pp = 0
+        # GroupNorm statistics from the producing GEMM epilogues (hi3d_gemm_params::gn_stats), as in the UNet plan
+        self.gn_unit = max(1, ae.cfg.ch // 32)
+        self.gn_fused = (os.environ.get("HI3D_GN_FUSED", "1") != "0" and ae.cfg.ch % 32 == 0
+                         and ae.cfg.ch * max(ae.cfg.ch_mult) // self.gn_unit <= 256)
+        self._stats_floats = 0
+        self.stats_arena = None
+        self._last_stats = {}          # id(LazyBuf) -> StatsBuf of the tensor it currently holds
+        if self.gn_fused:
+            self._call(lambda: self.stats_arena.zero_())
         if which == "enc":
             self._compile_encoder()
         elif which == "vdec":
@@ -45,6 +54,8 @@ class _VAEPlan:
         else:
             self._compile_decoder()
         self.A.materialise()
+        if self.gn_fused:
+            self.stats_arena = torch.zeros(max(self._stats_floats, 2), dtype=torch.float32, device=self.dev)
         self.steps = [b() for b in self._build]
         self._build = None
 
@@ -52,7 +63,7 @@ class _VAEPlan:
     def _gemm(self, segs_fn, W, out, M, **kw):
         def build():
             def res(v):
-                return v.t if isinstance(v, LazyBuf) else (v() if callable(v) else v)
+                return v.t if isinstance(v, (LazyBuf, StatsBuf)) else (v() if callable(v) else v)
             k2 = {k: res(v) for k, v in kw.items()}
             g = ops.Gemm(segs_fn(), res(W), res(out), M, engine=self.ae.engine, **k2)
             self.flops += g.flops
@@ -62,18 +73,36 @@ class _VAEPlan:
     def _call(self, fn):
         self._build.append(lambda: fn)
 
+    def _track(self, out: LazyBuf, C: int, rows_per_img: int) -> dict:
+        """Gemm kwargs: the epilogue accumulates the GroupNorm statistics of `out` (consumed by the next _gn on it)."""
+        if not self.gn_fused or C % 32 or C % self.gn_unit or C // self.gn_unit > 256:      # (C % 32: never a GroupNorm input)
+            self._last_stats.pop((out.tag, out.rows, out.cols), None)
+            return {}
+        sb = StatsBuf(self, self._stats_floats, self.n, C // self.gn_unit)
+        self._stats_floats += self.n * (C // self.gn_unit) * 2
+        self._last_stats[(out.tag, out.rows, out.cols)] = sb
+        return dict(gn_stats=sb, gn_unit=self.gn_unit, gn_rows=rows_per_img)
+
     def _nxt(self, rows, C):
         self._pp ^= 1
         return self.A.want(f"blk{self._pp}", rows, C)
 
-    def _gn(self, x: LazyBuf, key: str, rows_per_img: int, y: LazyBuf, silu=True):
+    def _gn(self, x: LazyBuf, key: str, rows_per_img: int, y: LazyBuf, silu=True, eps=1e-6, ips=1):
+        """GroupNorm(32)[+swish]; ips = images per sample (T for the (T,H,W) statistics of a time_stack)."""
         g, b = self.P[key]
-        self._call(lambda: ops.groupnorm_silu(x.t, None, self.n, rows_per_img, g, b, 1e-6, silu, y.t, self.gn_ws))
+        st = self._last_stats.get((x.tag, x.rows, x.cols))
+        ns, rows = self.n // ips, rows_per_img * ips
+        if st is not None:
+            self._call(lambda: ops.groupnorm_apply_stats(x.t, st.t, None, None, self.gn_unit, ns, rows, ips, rows, g, b, eps,
+                                                         silu, y.t))
+        else:
+            self._call(lambda: ops.groupnorm_silu(x.t, None, ns, rows, g, b, eps, silu, y.t, self.gn_ws))
 
     def _conv(self, src: LazyBuf, key: str, out: LazyBuf, ho, wo, hs, ws, stride=1, ups=0, pad_lo=1, **kw):
         Wt, b = self.P[key]
         self._gemm(lambda: ops.conv_taps([src.t], pad_lo=pad_lo), Wt, out, self.n * ho * wo, mode=ops.ROWS_CONV2D,
-                   geom=dict(Ho=ho, Wo=wo, Hs=hs, Ws=ws, stride=stride, ups=ups), bias=b, **kw)
+                   geom=dict(Ho=ho, Wo=wo, Hs=hs, Ws=ws, stride=stride, ups=ups), bias=b, **self._track(out, out.cols, ho * wo),
+                   **kw)
 
     def _resnet(self, pre: str, x: LazyBuf, cin: int, cout: int, h: int, w: int) -> LazyBuf:
         """ResnetBlock.forward, model.py:131-151 (temb is None)."""
@@ -87,9 +116,10 @@ class _VAEPlan:
         geo = dict(Ho=h, Wo=w, Hs=h, Ws=w)
         if cin != cout:    # nin_shortcut 1x1 as one more K segment over the raw input
             self._gemm(lambda: ops.conv_taps([g2.t]) + [ops.SegSpec(x.t)], Wt, out, M, mode=ops.ROWS_CONV2D, geom=geo,
-                       bias=b)
+                       bias=b, **self._track(out, cout, h * w))
         else:
-            self._gemm(lambda: ops.conv_taps([g2.t]), Wt, out, M, mode=ops.ROWS_CONV2D, geom=geo, bias=b, residual=x)
+            self._gemm(lambda: ops.conv_taps([g2.t]), Wt, out, M, mode=ops.ROWS_CONV2D, geom=geo, bias=b, residual=x,
+                       **self._track(out, cout, h * w))
         return out
 
     def _video_resnet(self, pre: str, x: LazyBuf, cin: int, cout: int, h: int, w: int) -> LazyBuf:
@@ -109,16 +139,14 @@ class _VAEPlan:
         geo = dict(Ho=HW, Wo=1, T=T)
         a = self.P[pre + "mix_factor"]
 
-        def gn(src, key, dst):
-            gg, bb = self.P[key]
-            self._call(lambda: ops.groupnorm_silu(src.t, None, B, T * HW, gg, bb, 1e-5, True, dst.t, self.gn_ws))
-        gn(xs, q + "in_layers.0", g)
+        self._gn(xs, q + "in_layers.0", HW, g, eps=1e-5, ips=T)
         W1, b1 = self.P[q + "in_layers.2"]
-        self._gemm(lambda: ops.temporal_taps(g.t), W1, hb, M, mode=ops.ROWS_TEMPORAL, geom=geo, bias=b1)
-        gn(hb, q + "out_layers.0", g)
+        self._gemm(lambda: ops.temporal_taps(g.t), W1, hb, M, mode=ops.ROWS_TEMPORAL, geom=geo, bias=b1,
+                   **self._track(hb, cout, HW))
+        self._gn(hb, q + "out_layers.0", HW, g, eps=1e-5, ips=T)
         W2, b2 = self.P[q + "out_layers.3"]
         self._gemm(lambda: ops.temporal_taps(g.t), W2, out, M, mode=ops.ROWS_TEMPORAL, geom=geo, bias=b2, residual=xs,
-                   blend_x=xs, alpha=1.0 - a)
+                   blend_x=xs, alpha=1.0 - a, **self._track(out, cout, HW))
         return out
 
     def _attn(self, pre: str, x: LazyBuf, C: int, h: int, w: int) -> LazyBuf:
@@ -143,7 +171,7 @@ class _VAEPlan:
             self._call(lambda: ops.softmax_rows(S.t, L, L, float(C) ** -0.5))
             self._gemm(lambda: [ops.SegSpec(S.t)], vt, lambda sl=sl: o.t[sl], L)
         Wo, bo = self.P[pre + "proj_out"]
-        self._gemm(lambda: [ops.SegSpec(o.t)], Wo, out, M, bias=bo, residual=x)
+        self._gemm(lambda: [ops.SegSpec(o.t)], Wo, out, M, bias=bo, residual=x, **self._track(out, C, L))
         return out
 
     # -- encoder / decoder walks ----------------------------------------------------------------------------------
@@ -208,10 +236,11 @@ class _VAEPlan:
             if lvl != 0:          # Upsample: nearest x2 + conv3x3 (model.py:67-71), fused into the gather
                 out = self._nxt(n * 4 * h * w, bi)
                 parity, ub = self.P[f"decoder.up.{lvl}.upsample.conv"]
+                trk = self._track(out, bi, h * w)               # one statistics table for the four parity launches
                 for (py, px), (Wt, shifts) in parity.items():   # nearest-x2 + conv3x3 == 4 parity-class 2x2 convs
                     self._gemm(lambda shifts=shifts, cur=cur: [ops.SegSpec(cur.t, dy=sy, dx=sx) for sy, sx in shifts], Wt,
                                out, n * h * w, mode=ops.ROWS_CONV2D,
-                               geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=ub)
+                               geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=ub, **trk)
                 cur, h, w = out, 2 * h, 2 * w
         M = n * h * w
         g = A.want("gn", M, bi)
