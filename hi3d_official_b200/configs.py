@@ -17,7 +17,32 @@ UNET_STAGE1 = dict(adm_in_channels=768, num_classes="sequential", use_checkpoint
 UNET_STAGE2 = dict(UNET_STAGE1, adm_in_channels=512, in_channels=17)
 
 
-def _model(stage: int) -> dict:
+def _emb_models(stage: int) -> list:
+    """conditioner_config.params.emb_models of configs/inference-v0{1,2}.yaml (:52-112 / :52-114)."""
+    clip = {"is_trainable": False, "input_key": "cond_frames_without_noise", "ucg_rate": 0.1,
+            "target": "sgm.modules.encoders.modules.FrozenOpenCLIPImagePredictionEmbedder",
+            "params": {"n_cond_frames": 1, "n_copies": 1, "open_clip_embedding_config": {
+                "target": "sgm.modules.encoders.modules.FrozenOpenCLIPImageEmbedder",
+                "params": {"version": "ckpts/open_clip_pytorch_model.bin", "freeze": True}}}}
+
+    def ts(key):
+        return {"is_trainable": False, "input_key": key, "target": "sgm.modules.encoders.modules.ConcatTimestepEmbedderND",
+                "params": {"outdim": 256}}
+    vae = {"input_key": "cond_frames", "is_trainable": False, "ucg_rate": 0.1,
+           "target": "sgm.modules.encoders.modules.VideoPredictionEmbedderWithEncoder",
+           "params": {"disable_encoder_autocast": True, "n_cond_frames": 1, "n_copies": 16 if stage == 1 else 1, "is_ae": True,
+                      "encoder_config": {"target": "sgm.models.autoencoder.AutoencoderKLModeOnly", "params": {
+                          "embed_dim": 4, "monitor": "val/rec_loss", "ddconfig": copy.deepcopy(_VAE_DD),
+                          "lossconfig": {"target": "torch.nn.Identity"}}}}}
+    if stage == 1:
+        aes = {"is_trainable": False, "input_key": "video", "ucg_rate": 0.0, "target": "vtdm.encoders.AesEmbedder"}
+        return [clip, aes, ts("elevation"), vae, ts("cond_aug")]
+    depth = {"is_trainable": False, "input_key": "cond_frames", "ucg_rate": 0.0, "target": "vtdm.encoders.DepthEmbedder",
+             "params": {"shuffle_size": 3}}
+    return [clip, ts("elevation"), depth, vae, ts("cond_aug")]
+
+
+def _model(stage: int, conditioner: bool = False) -> dict:
     unet = UNET_STAGE1 if stage == 1 else UNET_STAGE2
     return {
         "target": "vtdm.vtdm_gen_v01.VideoLDM" if stage == 1 else "vtdm.vtdm_gen_stage2_degradeImage.VideoLDM",
@@ -29,7 +54,10 @@ def _model(stage: int) -> dict:
                 "scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"}}},
             "network_config": {"target": "sgm.modules.diffusionmodules.video_model.VideoUNet",
                                "params": copy.deepcopy(unet)},
-            "conditioner_config": {"target": "sgm.modules.GeneralConditioner", "params": {"emb_models": []}},
+            # benches / parity tests feed ready-made conditioning: no embedders unless asked for (each run would carry a
+            # second VAE encoder for the cond-frame latents)
+            "conditioner_config": {"target": "sgm.modules.GeneralConditioner",
+                                   "params": {"emb_models": _emb_models(stage) if conditioner else []}},
             "first_stage_config": {"target": "sgm.models.autoencoder.AutoencoderKL", "params": {
                 "embed_dim": 4, "monitor": "val/rec_loss", "ddconfig": copy.deepcopy(_VAE_DD),
                 "lossconfig": {"target": "torch.nn.Identity"}}},
@@ -44,12 +72,12 @@ def _model(stage: int) -> dict:
     }
 
 
-def stage1_config() -> dict:
-    return {"model": _model(1)}
+def stage1_config(conditioner: bool = False) -> dict:
+    return {"model": _model(1, conditioner)}
 
 
-def stage2_config() -> dict:
-    return {"model": _model(2)}
+def stage2_config(conditioner: bool = False) -> dict:
+    return {"model": _model(2, conditioner)}
 
 
 def build_engine(stage: int = 1, device="cuda", unet_overrides=None, vae_overrides=None, num_steps=None,

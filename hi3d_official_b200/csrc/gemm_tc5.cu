@@ -158,8 +158,22 @@ HI3D_DEVINL long long t5_map(const T5Params& p, long long m) {
 // NCTA = 2: the two CTAs of a cluster own the two 128-row halves of a 256-row tile and half of the B tile each;
 // CTA 0 issues tcgen05.mma.cta_group::2 for the pair (operands are read from both CTAs' shared memory, so every B
 // byte is fetched from L2 once per PAIR), each CTA runs the epilogue of its own 128 accumulator rows.
-template <int NCTA>
+// EPI specialises the epilogue at compile time.  The generic epilogue (EPI_GENERIC: every option a run-time branch on a
+// kernel parameter) was profiled at 12 % instruction-cache misses and 6 % branch stalls on the short-K GEMMs, whose epilogue
+// IS the kernel (ncu source page, profiles/r02_ncu_gemm_epilogue_notes.txt): the options that cost code and branches inside the
+// chunk loop -- GEGLU, residual, blend, GroupNorm statistics -- are template constants in the specialised kernels.
+enum { EPI_GENERIC = 0, EPI_GEGLU = 1, EPI_BIAS = 2, EPI_RES = 3, EPI_RESBLEND = 4, EPI_BIAS_GN = 5, EPI_RES_GN = 6, EPI_RESBLEND_GN = 7 };
+
+template <int NCTA, int EPI>
 __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ T5Params p) {
+  constexpr bool kGen = (EPI == EPI_GENERIC);
+  // compile-time constants in the specialised kernels, run-time tests in the generic one
+  const bool kGeglu = kGen ? (p.act == HI3D_ACT_GEGLU) : (EPI == EPI_GEGLU);
+  const bool kRes = kGen ? (p.residual != nullptr) : (EPI == EPI_RES || EPI == EPI_RESBLEND || EPI == EPI_RES_GN || EPI == EPI_RESBLEND_GN);
+  const bool kBlend = kGen ? (p.blend_x != nullptr) : (EPI == EPI_RESBLEND || EPI == EPI_RESBLEND_GN);
+  const bool kSilu = kGen ? (p.act == HI3D_ACT_SILU) : false;
+  const bool kGn = kGen ? (p.gn_stats != nullptr && p.act != HI3D_ACT_GEGLU) : (EPI >= EPI_BIAS_GN);
+  const int kDbg = kGen ? p.dbg : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024-byte alignment
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
     // single-thread issue loops -- ~600 cycles per k-block -- were the slowest part of the kernel.)
     uint32_t s = 0, ph = 0;
     const uint32_t lead_full = (NCTA == 2) ? mapa_cluster(bar_full, 0) : bar_full;   // pair: bytes count on CTA 0
-    const uint32_t txb = ((p.dbg & 16) ? 0u : (uint32_t)T5_A_BYTES) + ((p.dbg & 32) ? 0u : (uint32_t)(BN / NCTA) * 128u);
+    const uint32_t txb = ((kDbg & 16) ? 0u : (uint32_t)T5_A_BYTES) + ((kDbg & 32) ? 0u : (uint32_t)(BN / NCTA) * 128u);
     for (int tile = unit0; tile < p.total_tiles; tile += nunits) {
       const int mu = tile / p.n_tiles, nt = tile - mu * p.n_tiles;
       const int mt = mu * NCTA + (int)rank;
@@ -236,25 +250,25 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
             // tx-count goes negative for a moment), and a release.cluster arrive per k-block serialises the producer.
             const uint32_t full = lead_full + 8 * s;
             if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2 * txb);
-            if (p.dbg & 16) {
+            if (kDbg & 16) {
             } else if (p.mode == HI3D_ROWS_PLAIN)
               tma_load_2d_cg2(sA, am, full, c, mt * T5_BM);
             else if (p.mode == HI3D_ROWS_CONV2D)
               tma_load_4d_cg2(sA, am, full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
             else
               tma_load_4d_cg2(sA, am, full, c, o.x0, o.y0 + p.t_off + sg.dt, o.z0);
-            if (!(p.dbg & 32)) tma_load_2d_cg2(sB, &p.bmap, full, kt * T5_BK, n0);
+            if (!(kDbg & 32)) tma_load_2d_cg2(sB, &p.bmap, full, kt * T5_BK, n0);
           } else {
             const uint32_t full = bar_full + 8 * s;
             mbar_expect_tx(full, txb);
-            if (p.dbg & 16) {
+            if (kDbg & 16) {
             } else if (p.mode == HI3D_ROWS_PLAIN)
               tma_load_2d(sA, am, full, c, mt * T5_BM);
             else if (p.mode == HI3D_ROWS_CONV2D)
               tma_load_4d(sA, am, full, c, o.x0 * p.cstride + sg.dx, o.y0 * p.cstride + sg.dy, o.z0);
             else
               tma_load_4d(sA, am, full, c, o.x0, o.y0 + p.t_off + sg.dt, o.z0);
-            if (!(p.dbg & 32)) tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
+            if (!(kDbg & 32)) tma_load_2d(sB, &p.bmap, full, kt * T5_BK, n0);
           }
         }
         __syncwarp();
@@ -289,7 +303,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           tc_fence_after();
           if (elect_one()) {
             const uint64_t ad = ad0 + (uint64_t)(s * stage16), bd = bd0 + (uint64_t)(s * stage16);
-            if (!(p.dbg & 8)) {
+            if (!(kDbg & 8)) {
 #pragma unroll
               for (int k = 0; k < T5_BK / 16; k++) {   // +32 bytes along K inside the 128-byte swizzle atom
                 if (NCTA == 2) tc_mma_f16_cg2(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kt | k) ? 1u : 0u);
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int ew = warp - 2;                     // epilogue warp index
     const int wsel = ew >> 2;                    // this warp takes 32-column chunks wsel, wsel + EPI/4, ...
-    const bool geglu = (p.act == HI3D_ACT_GEGLU);
+    const bool geglu = kGeglu;
     const int rl = q * 32 + lane;                // tile-local row == TMEM lane
     uint8_t* scr = scratch + ew * T5_SCR_BYTES;  // 32 rows x 80 bytes (64 data + 16 pad)
     const int crow = lane >> 2, cchk = lane & 3; // coalesced pattern: rows crow + 8 i, 16-byte chunk cchk
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       const int nb = (unit0 % p.n_tiles) * BN + et;
       sbias[et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
     }
-    const bool gn_on = (p.gn_stats != nullptr) && !geglu;
+    const bool gn_on = kGn;
     const int gn_tab_n = gn_on ? p.gn_spt * p.gn_upt * 2 : 0;
     for (int i = et; i < gn_tab_n; i += 32 * T5_EPI_WARPS) gn_tab[i] = 0.f;      // visible after the first bar.sync below
     for (int tile = unit0; tile < p.total_tiles; tile += nunits, at++) {
@@ -377,24 +391,24 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
 #pragma unroll 1
       for (int c0 = wsel * 32; c0 < BN; c0 += 8 * T5_EPI_WARPS) {
         uint32_t v[32];
-        if (!(p.dbg & 4)) tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
+        if (!(kDbg & 4)) tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
         const int n = n0 + c0;
         const bool live = (m >= 0) && (n < p.N);
         const bool colok = (n + cchk * 8) < p.N;                   // this lane's 16-byte column group exists
         // issue every global load of this chunk (coalesced pattern) while the TMEM read is in flight
         Half8 rb8[4], rsg[4], bxg[4];
-        if (!(p.dbg & 2)) {
+        if (!(kDbg & 2)) {
           if (rbp != nullptr && live) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
               if (n + 8 * j < p.N) rb8[j] = *reinterpret_cast<const Half8*>(rbp + n + 8 * j);
           }
-          if (p.residual != nullptr) {
+          if (kRes) {
 #pragma unroll
             for (int i = 0; i < 4; i++)
               if (mrow[i] >= 0 && colok) rsg[i] = *reinterpret_cast<const Half8*>(p.residual + mrow[i] * p.res_ld + n + cchk * 8);
           }
-          if (p.blend_x != nullptr) {
+          if (kBlend) {
 #pragma unroll
             for (int i = 0; i < 4; i++)
               if (mrow[i] >= 0 && colok) bxg[i] = *reinterpret_cast<const Half8*>(p.blend_x + mrow[i] * p.blend_ld + n + cchk * 8);
@@ -437,12 +451,12 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
             const int rr = (lane >> 1) + 16 * i, ck = lane & 1;
             const long long mr = __shfl_sync(0xffffffffu, m, rr);
             const Half8 w8 = *reinterpret_cast<const Half8*>(scr + rr * 80 + ck * 16);
-            if (mr >= 0 && n + 16 * ck < p.N && !(p.dbg & 1))
+            if (mr >= 0 && n + 16 * ck < p.N && !(kDbg & 1))
               *reinterpret_cast<Half8*>(p.out + mr * p.out_ld + (n >> 1) + 8 * ck) = w8;
           }
           __syncwarp();
         } else {
-          if (p.act == HI3D_ACT_SILU) {
+          if (kSilu) {
 #pragma unroll
             for (int j = 0; j < 32; j++) f[j] = silu_f(f[j]);
           }
@@ -463,21 +477,21 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
           for (int i = 0; i < 4; i++) {
             Half8& w8 = w8s[i];
             if (mrow[i] < 0 || !colok) continue;
-            if (p.residual != nullptr && !(p.dbg & 2)) {
+            if (kRes && !(kDbg & 2)) {
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const float2 a = __half22float2(w8.h[k]), b = __half22float2(rsg[i].h[k]);
                 w8.h[k] = __floats2half2_rn(a.x + b.x, a.y + b.y);
               }
             }
-            if (p.blend_x != nullptr && !(p.dbg & 2)) {
+            if (kBlend && !(kDbg & 2)) {
 #pragma unroll
               for (int k = 0; k < 4; k++) {
                 const float2 a = __half22float2(w8.h[k]), b = __half22float2(bxg[i].h[k]);
                 w8.h[k] = __floats2half2_rn(al * b.x + be * a.x, al * b.y + be * a.y);
               }
             }
-            if (!(p.dbg & 1)) *reinterpret_cast<Half8*>(p.out + mrow[i] * p.out_ld + n + cchk * 8) = w8;
+            if (!(kDbg & 1)) *reinterpret_cast<Half8*>(p.out + mrow[i] * p.out_ld + n + cchk * 8) = w8;
           }
           __syncwarp();
           if (gn_on) {
@@ -635,6 +649,47 @@ static void read_env_once() {
   if (g_dbg < 0) { const char* e = getenv("HI3D_TC5_DBG"); g_dbg = e ? atoi(e) : 0; }
 }
 
+template <int NCTA, int EPI>
+static int launch_tc5_one(const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
+  static bool attr_done[HI3D_MAX_DEVICES];
+  if (ensure_dyn_smem(gemm_tc5_kernel<NCTA, EPI>, smem_total, attr_done, "hi3d_gemm_tc5")) return -1;
+  if (NCTA == 2) {
+    const int grid = 2 * (tp.total_tiles < units ? tp.total_tiles : units);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T5_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<2, EPI>, tp);
+    if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: pair launch: %s", cudaGetErrorString(e)); return -1; }
+  } else {
+    const int grid = tp.total_tiles < sm_count ? tp.total_tiles : sm_count;
+    gemm_tc5_kernel<1, EPI><<<grid, T5_THREADS, smem, st>>>(tp);
+  }
+  return 0;
+}
+
+template <int NCTA>
+static int launch_tc5_n(int epi, const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
+  switch (epi) {
+    case EPI_GEGLU: return launch_tc5_one<NCTA, EPI_GEGLU>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_BIAS: return launch_tc5_one<NCTA, EPI_BIAS>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RES: return launch_tc5_one<NCTA, EPI_RES>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RESBLEND: return launch_tc5_one<NCTA, EPI_RESBLEND>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_BIAS_GN: return launch_tc5_one<NCTA, EPI_BIAS_GN>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RES_GN: return launch_tc5_one<NCTA, EPI_RES_GN>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RESBLEND_GN: return launch_tc5_one<NCTA, EPI_RESBLEND_GN>(tp, smem, smem_total, units, sm_count, st);
+    default: return launch_tc5_one<NCTA, EPI_GENERIC>(tp, smem, smem_total, units, sm_count, st);
+  }
+}
+
+static int launch_tc5(int ncta, int epi, const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
+  return ncta == 2 ? launch_tc5_n<2>(epi, tp, smem, smem_total, units, sm_count, st)
+                   : launch_tc5_n<1>(epi, tp, smem, smem_total, units, sm_count, st);
+}
+
 }  // namespace hi3d
 
 using namespace hi3d;
@@ -789,25 +844,18 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.out = (__half*)p->out; tp.out_ld = p->out_ld;
   tp.dbg = g_dbg;
 
-  static bool attr_done1[HI3D_MAX_DEVICES], attr_done2[HI3D_MAX_DEVICES];
   const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
-  if (ensure_dyn_smem(gemm_tc5_kernel<1>, smem_total, attr_done1, "hi3d_gemm_tc5") ||
-      ensure_dyn_smem(gemm_tc5_kernel<2>, smem_total, attr_done2, "hi3d_gemm_tc5")) return -1;
   const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + gn_tab_bytes + 1024;
-  if (ncta == 2) {
-    const int grid = 2 * (tp.total_tiles < units ? tp.total_tiles : units);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T5_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<2>, tp);
-    if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: pair launch: %s", cudaGetErrorString(e)); return -1; }
-  } else {
-    const int grid = tp.total_tiles < g_sm_count ? tp.total_tiles : g_sm_count;
-    gemm_tc5_kernel<1><<<grid, T5_THREADS, smem, st>>>(tp);
+  // epilogue specialisation
+  int epi = EPI_GENERIC;
+  const bool has_res = p->residual != nullptr, has_blend = p->blend_x != nullptr, has_gn = p->gn_stats != nullptr;
+  if (tp.dbg == 0 && p->act != HI3D_ACT_SILU && !(has_blend && !has_res)) {
+    if (p->act == HI3D_ACT_GEGLU) epi = (has_res || has_blend || has_gn) ? EPI_GENERIC : EPI_GEGLU;
+    else if (has_blend) epi = has_gn ? EPI_RESBLEND_GN : EPI_RESBLEND;
+    else if (has_res) epi = has_gn ? EPI_RES_GN : EPI_RES;
+    else epi = has_gn ? EPI_BIAS_GN : EPI_BIAS;
   }
+  rc = launch_tc5(ncta, epi, tp, smem, smem_total, units, g_sm_count, st);
+  if (rc) return rc;
   return check_launch("hi3d_gemm_tc5");
 }

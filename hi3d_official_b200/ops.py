@@ -217,6 +217,14 @@ def attention_d64(qkv: torch.Tensor, n_img: int, L: int, heads: int, out: torch.
     N.check(fn(qkv.data_ptr(), n_img, L, heads, scale, out.data_ptr(), _stream()), "hi3d_attention_d64")
 
 
+def attention_d512(qkv: torch.Tensor, n_img: int, L: int, out: torch.Tensor, scale: float = 512 ** -0.5):
+    """VAE AttnBlock core: one head of dimension 512, qkv fp16 [n_img*L, 1536] -> out fp16 [n_img*L, 512]."""
+    _chk16(qkv, "qkv"); _chk16(out, "out")
+    if qkv.shape[-1] != 1536 or out.shape[-1] != 512:
+        raise ValueError("attention_d512: qkv must be [rows, 1536], out [rows, 512]")
+    N.check(N.load().hi3d_attention_d512_tc5(qkv.data_ptr(), n_img, L, scale, out.data_ptr(), _stream()), "hi3d_attention_d512_tc5")
+
+
 def temporal_attention_d64(qkv: torch.Tensor, B: int, T: int, S: int, heads: int, out: torch.Tensor,
                            scale: float = 0.125):
     _chk16(qkv, "qkv"); _chk16(out, "out")

@@ -154,9 +154,22 @@ class _VAEPlan:
         scores = GEMM(q, k) -> row softmax -> GEMM(P, v^T) on the same engine as everything else."""
         n, L = self.n, h * w
         M = n * L
+        A = self.A
+        if C == 512 and L % 128 == 0 and self.ae.engine == "tc5":
+            # flash attention on tcgen05: q|k|v as ONE GEMM, fp32 scores / softmax inside the kernel, no L x L buffer
+            g, qkv, o = A.want("gn", M, C), A.want("qkv", M, 3 * C), A.want("att", M, C)
+            out = self._nxt(M, C)
+            self._gn(x, pre + "norm", L, g, silu=False)
+            Wq, bq = self.P[pre + "qkv"]
+            self._gemm(lambda: [ops.SegSpec(g.t)], Wq, qkv, M, bias=bq)
+            self._call(lambda: ops.attention_d512(qkv.t, n, L, o.t, float(C) ** -0.5))
+            Wo, bo = self.P[pre + "proj_out"]
+            self._gemm(lambda: [ops.SegSpec(o.t)], Wo, out, M, bias=bo, residual=x, **self._track(out, C, L))
+            return out
+        # small / odd sizes (L not a multiple of 128) and the mma.sync engine: scores through the GEMM engine, one image at a
+        # time (an L x L fp16 buffer -- fine for the tiny test shapes this path still serves)
         if L % 64:
             raise NotImplementedError(f"VAE attention needs (H/8)*(W/8) % 64 == 0, got {L}")
-        A = self.A
         g, q, k, v, o = (A.want(t, M, C) for t in ("gn", "q", "k", "v", "att"))
         S, vt = A.want("scores", L, L), A.want("vt", C, L)
         out = self._nxt(M, C)
@@ -374,6 +387,10 @@ class AutoencoderKL(nn.Module):
                 P[base] = (pack.cat_k(pack.pack_conv2d(w), pack.pack_conv2d(ws_)), (b.float() + bs_.float()).contiguous())
             else:
                 P[base] = (pack.pack_conv2d(w), b.float().contiguous())
+        for pre in ("encoder.mid.attn_1.", "decoder.mid.attn_1."):      # q | k | v of the AttnBlock as one [3C, C] GEMM
+            if pre + "q" in P:
+                P[pre + "qkv"] = (torch.cat([P[pre + n_][0] for n_ in "qkv"], 0).contiguous(),
+                                  torch.cat([P[pre + n_][1] for n_ in "qkv"], 0).contiguous())
         self._packed = P
         return P
 

@@ -211,6 +211,12 @@ int hi3d_temporal_attention_d64(const void* qkv, int B, int T, int S, int heads,
 int hi3d_temporal_attention_d64_sharded(void* const* qkv_of_rank, void* const* out_of_rank, int rank, int world, int B,
                                         int T_local, int S, int heads, float scale, void* stream);
 
+/* VAE mid-block attention (AttnBlock, model.py:180-201; xformers path model.py:204-265): ONE head of dimension 512,
+ * softmax(q k^T * scale) v per image with scale = 512^-0.5, as a flash-attention kernel (tcgen05 / TMEM / TMA): fp32
+ * scores and softmax, no L x L matrix in memory.  qkv: fp16 [n_img*L, 1536] = q | k | v column blocks (the three 1x1 convs as
+ * one GEMM); out fp16 [n_img*L, 512].  L must be a multiple of 128 ((H/8)*(W/8) at every Hi3D size). */
+int hi3d_attention_d512_tc5(const void* qkv, int n_img, int L, float scale, void* out, void* stream);
+
 /* Row softmax in place on fp16 [rows, L] (scores * scale), and 2-D transpose [R, Cc] -> [Cc, R] (fp16):
  * building blocks of the VAE single-head d=512 attention (model.py:180-195) on top of hi3d_gemm. */
 int hi3d_softmax_rows(void* s, int64_t rows, int L, float scale, void* stream);

@@ -363,3 +363,24 @@ def test_fused_heun_and_dpmpp2m_match_generic_path():
 def N_launches():
     from hi3d_official_b200 import _native
     return _native.launch_count()
+
+
+@pytest.mark.parametrize("n_img,L,qscale", [(2, 256, 1.0), (1, 4096, 1.0), (1, 16384, 1.0), (2, 1024, 4.0), (1, 512, 0.2)])
+def test_attention_d512_flash(n_img, L, qscale):
+    """hi3d_attention_d512_tc5 (VAE AttnBlock core, model.py:180-201): one head of dimension 512, fp32 scores inside the
+    kernel, no L x L buffer -- against fp32 softmax(q k^T / sqrt(512)) v, up to L = 16384 (the 1024^2 VAE) and with logits
+    large enough (|s| ~ 60) that fp16 scores would lose the parity."""
+    qkv = rnd(n_img * L, 3, 512, seed=L + n_img)
+    qkv[:, 0] *= qscale
+    pos = torch.arange(n_img * L, device=DEV, dtype=torch.float32) % L / L
+    qkv[:, 1] *= (0.5 + 1.5 * pos)[:, None]                 # keys grow along the sequence: the reference maximum moves
+    qkv = qkv.reshape(n_img * L, 1536).to(H)
+    out = torch.zeros(n_img * L, 512, dtype=H, device=DEV)
+    ops.attention_d512(qkv, n_img, L, out)
+    q, k, v = (t.reshape(n_img, L, 512).float() for t in qkv.view(n_img * L, 3, 512).unbind(1))
+    ref = torch.empty(n_img, L, 512, device=DEV)
+    for i in range(n_img):
+        for r0 in range(0, L, 2048):
+            s_ = q[i, r0:r0 + 2048] @ k[i].t() * 512 ** -0.5
+            ref[i, r0:r0 + 2048] = torch.softmax(s_, -1) @ v[i]
+    close(out.view(n_img, L, 512), ref, atol=2e-3, name=f"flash d512 L={L}")
