@@ -50,6 +50,7 @@ _SIGS = {
     "hi3d_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "hi3d_gemm_tc5": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "hi3d_gemm_tc5_set_pair_mode": (C.c_int, [C.c_int]),
+    "hi3d_gemm_tc5_set_epilogue_warps": (C.c_int, [C.c_int]),
     "hi3d_groupnorm_ws_floats": (C.c_int64, [C.c_int]),
     "hi3d_groupnorm_silu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

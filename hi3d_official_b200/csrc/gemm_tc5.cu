@@ -164,8 +164,11 @@ HI3D_DEVINL long long t5_map(const T5Params& p, long long m) {
 // chunk loop -- GEGLU, residual, blend, GroupNorm statistics -- are template constants in the specialised kernels.
 enum { EPI_GENERIC = 0, EPI_GEGLU = 1, EPI_BIAS = 2, EPI_RES = 3, EPI_RESBLEND = 4, EPI_BIAS_GN = 5, EPI_RES_GN = 6, EPI_RESBLEND_GN = 7 };
 
-template <int NCTA, int EPI>
-__global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_constant__ T5Params p) {
+// EW = epilogue warps (8 or 16).  Sixteen (four per TMEM lane quarter, every fourth 32-column chunk each) double the
+// epilogue's issue slots and loads / stores in flight for the short-K GEMMs whose epilogue is the bound; the register-light
+// specialisations (<= 112 registers) fit 576 threads.
+template <int NCTA, int EPI, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_constant__ T5Params p) {
   constexpr bool kGen = (EPI == EPI_GENERIC);
   // compile-time constants in the specialised kernels, run-time tests in the generic one
   const bool kGeglu = kGen ? (p.act == HI3D_ACT_GEGLU) : (EPI == EPI_GEGLU);
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       reinterpret_cast<volatile uint32_t*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 32);
   float* sbias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64);   // [2][256]
   uint8_t* scratch = smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048;                  // [EPI_WARPS][32 x 80]
-  float* gn_tab = reinterpret_cast<float*>(scratch + T5_EPI_WARPS * T5_SCR_BYTES);                  // [gn_spt][gn_upt][2]
+  float* gn_tab = reinterpret_cast<float*>(scratch + EW * T5_SCR_BYTES);                  // [gn_spt][gn_upt][2]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role index
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(bar_acc_full + 8 * b, 1);
-      mbar_init(bar_acc_empty + 8 * b, T5_EPI_WARPS * NCTA);   // pair: both CTAs' epilogue warps report to the leader
+      mbar_init(bar_acc_empty + 8 * b, EW * NCTA);   // pair: both CTAs' epilogue warps report to the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -343,11 +346,11 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
     // barrier per tile was on the critical path of every epilogue warp)
     if (unit0 < p.total_tiles) {
       const int nb = (unit0 % p.n_tiles) * BN + et;
-      sbias[et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
+      if (et < 256) sbias[et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
     }
     const bool gn_on = kGn;
     const int gn_tab_n = gn_on ? p.gn_spt * p.gn_upt * 2 : 0;
-    for (int i = et; i < gn_tab_n; i += 32 * T5_EPI_WARPS) gn_tab[i] = 0.f;      // visible after the first bar.sync below
+    for (int i = et; i < gn_tab_n; i += 32 * EW) gn_tab[i] = 0.f;      // visible after the first bar.sync below
     for (int tile = unit0; tile < p.total_tiles; tile += nunits, at++) {
       const int mu = tile / p.n_tiles, nt = tile - mu * p.n_tiles;
       const int mt = mu * NCTA + (int)rank;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       const uint32_t buf = at & 1;
       // every epilogue warp has finished the previous tile (its bias buffer may be overwritten) and this tile's slice,
       // written during the previous tile, is visible
-      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T5_EPI_WARPS) : "memory");
+      asm volatile("bar.sync 1, %0;\n" ::"n"(32 * EW) : "memory");
       float bnext = 0.f;
       {
         const int tnext = tile + nunits;
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c0 = wsel * 32; c0 < BN; c0 += 8 * T5_EPI_WARPS) {
+      for (int c0 = wsel * 32; c0 < BN; c0 += 8 * EW) {
         uint32_t v[32];
         if (!(kDbg & 4)) tmem_ld32(tacc + (uint32_t)c0, v);       // asynchronous: completes at tmem_ld_wait()
         const int n = n0 + c0;
@@ -574,9 +577,9 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
       }
       if (gn_on) {
         // every epilogue warp has added its chunks of this tile: flush the table (one global atomic per touched entry)
-        asm volatile("bar.sync 2, %0;\n" ::"n"(32 * T5_EPI_WARPS) : "memory");
+        asm volatile("bar.sync 2, %0;\n" ::"n"(32 * EW) : "memory");
         const int u0 = n0 / p.gn_unit;
-        for (int i = et; i < gn_tab_n; i += 32 * T5_EPI_WARPS) {
+        for (int i = et; i < gn_tab_n; i += 32 * EW) {
           const float v = gn_tab[i];
           if (v != 0.f) {
             const int which = i & 1, ent = i >> 1;
@@ -587,7 +590,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) gemm_tc5_kernel(const __grid_co
         }
         // (the bar.sync 1 at the top of the next tile orders these zeroing stores before the next tile's atomics)
       }
-      sbias[(buf ^ 1) * 256 + et] = bnext;      // next tile's slice -> the buffer nobody reads until the next bar.sync
+      if (et < 256) sbias[(buf ^ 1) * 256 + et] = bnext;      // next tile's slice -> the buffer nobody reads until the next bar.sync
       // this warp is done reading the accumulator buffer
       tc_fence_before();
       __syncwarp();
@@ -644,50 +647,59 @@ static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 // in the un-graphed frame-sharded mode); hi3d_gemm_tc5_set_pair_mode overrides the pair knob for tests
 static int g_pair_mode = -2;      // -2 unread, -1 auto, 0 single CTA, 1 CTA pairs
 static int g_dbg = -1;            // -1 unread
+static int g_ew_mode = -2;        // -2 unread, -1 auto, 8 / 16 forced (HI3D_TC5_EW)
+constexpr int T5_EW16_MAX_K = 640;
 static void read_env_once() {
   if (g_pair_mode == -2) { const char* e = getenv("HI3D_TC5_PAIR"); g_pair_mode = e ? atoi(e) : -1; }
   if (g_dbg < 0) { const char* e = getenv("HI3D_TC5_DBG"); g_dbg = e ? atoi(e) : 0; }
+  if (g_ew_mode == -2) { const char* e = getenv("HI3D_TC5_EW"); g_ew_mode = e ? atoi(e) : -1; if (g_ew_mode != 8 && g_ew_mode != 16) g_ew_mode = -1; }
 }
 
-template <int NCTA, int EPI>
+template <int NCTA, int EPI, int EW>
 static int launch_tc5_one(const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
   static bool attr_done[HI3D_MAX_DEVICES];
-  if (ensure_dyn_smem(gemm_tc5_kernel<NCTA, EPI>, smem_total, attr_done, "hi3d_gemm_tc5")) return -1;
+  if (ensure_dyn_smem(gemm_tc5_kernel<NCTA, EPI, EW>, smem_total, attr_done, "hi3d_gemm_tc5")) return -1;
+  constexpr int THREADS = 64 + 32 * EW;
   if (NCTA == 2) {
     const int grid = 2 * (tp.total_tiles < units ? tp.total_tiles : units);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T5_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<2, EPI>, tp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5_kernel<2, EPI, EW>, tp);
     if (e != cudaSuccess) { set_error("hi3d_gemm_tc5: pair launch: %s", cudaGetErrorString(e)); return -1; }
   } else {
     const int grid = tp.total_tiles < sm_count ? tp.total_tiles : sm_count;
-    gemm_tc5_kernel<1, EPI><<<grid, T5_THREADS, smem, st>>>(tp);
+    gemm_tc5_kernel<1, EPI, EW><<<grid, THREADS, smem, st>>>(tp);
   }
   return 0;
 }
 
 template <int NCTA>
-static int launch_tc5_n(int epi, const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
+static int launch_tc5_n(int epi, int ew, const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
+  if (ew == 16) {      // only the register-light specialisations exist with 16 epilogue warps
+    if (epi == EPI_GEGLU) return launch_tc5_one<NCTA, EPI_GEGLU, 16>(tp, smem, smem_total, units, sm_count, st);
+    if (epi == EPI_BIAS) return launch_tc5_one<NCTA, EPI_BIAS, 16>(tp, smem, smem_total, units, sm_count, st);
+  }
   switch (epi) {
-    case EPI_GEGLU: return launch_tc5_one<NCTA, EPI_GEGLU>(tp, smem, smem_total, units, sm_count, st);
-    case EPI_BIAS: return launch_tc5_one<NCTA, EPI_BIAS>(tp, smem, smem_total, units, sm_count, st);
-    case EPI_RES: return launch_tc5_one<NCTA, EPI_RES>(tp, smem, smem_total, units, sm_count, st);
-    case EPI_RESBLEND: return launch_tc5_one<NCTA, EPI_RESBLEND>(tp, smem, smem_total, units, sm_count, st);
-    case EPI_BIAS_GN: return launch_tc5_one<NCTA, EPI_BIAS_GN>(tp, smem, smem_total, units, sm_count, st);
-    case EPI_RES_GN: return launch_tc5_one<NCTA, EPI_RES_GN>(tp, smem, smem_total, units, sm_count, st);
-    case EPI_RESBLEND_GN: return launch_tc5_one<NCTA, EPI_RESBLEND_GN>(tp, smem, smem_total, units, sm_count, st);
-    default: return launch_tc5_one<NCTA, EPI_GENERIC>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_GEGLU: return launch_tc5_one<NCTA, EPI_GEGLU, 8>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_BIAS: return launch_tc5_one<NCTA, EPI_BIAS, 8>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RES: return launch_tc5_one<NCTA, EPI_RES, 8>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RESBLEND: return launch_tc5_one<NCTA, EPI_RESBLEND, 8>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_BIAS_GN: return launch_tc5_one<NCTA, EPI_BIAS_GN, 8>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RES_GN: return launch_tc5_one<NCTA, EPI_RES_GN, 8>(tp, smem, smem_total, units, sm_count, st);
+    case EPI_RESBLEND_GN: return launch_tc5_one<NCTA, EPI_RESBLEND_GN, 8>(tp, smem, smem_total, units, sm_count, st);
+    default: return launch_tc5_one<NCTA, EPI_GENERIC, 8>(tp, smem, smem_total, units, sm_count, st);
   }
 }
 
-static int launch_tc5(int ncta, int epi, const T5Params& tp, int smem, int smem_total, int units, int sm_count, cudaStream_t st) {
-  return ncta == 2 ? launch_tc5_n<2>(epi, tp, smem, smem_total, units, sm_count, st)
-                   : launch_tc5_n<1>(epi, tp, smem, smem_total, units, sm_count, st);
+static int launch_tc5(int ncta, int epi, int ew, const T5Params& tp, int smem, int smem_total, int units, int sm_count,
+                      cudaStream_t st) {
+  return ncta == 2 ? launch_tc5_n<2>(epi, ew, tp, smem, smem_total, units, sm_count, st)
+                   : launch_tc5_n<1>(epi, ew, tp, smem, smem_total, units, sm_count, st);
 }
 
 }  // namespace hi3d
@@ -698,6 +710,13 @@ extern "C" int hi3d_gemm_tc5_set_pair_mode(int mode) {
   if (mode < -1 || mode > 1) { set_error("hi3d_gemm_tc5_set_pair_mode: mode must be -1 (auto), 0 or 1"); return -2; }
   read_env_once();
   g_pair_mode = mode;
+  return 0;
+}
+
+extern "C" int hi3d_gemm_tc5_set_epilogue_warps(int warps) {
+  if (warps != -1 && warps != 8 && warps != 16) { set_error("hi3d_gemm_tc5_set_epilogue_warps: -1 (auto), 8 or 16"); return -2; }
+  read_env_once();
+  g_ew_mode = warps;
   return 0;
 }
 
@@ -802,8 +821,21 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     gn_tab_bytes = tp.gn_spt * tp.gn_upt * 2 * (int)sizeof(float);
     if (gn_tab_bytes > 24 * 1024) return hi3d_gemm(p, stream);      // tiny images: the mma engine + a separate statistics pass
   }
+  // epilogue specialisation and epilogue warp count (decided here: the scratch of 16 warps comes out of the stage budget)
+  int epi = EPI_GENERIC;
+  const bool has_res = p->residual != nullptr, has_blend = p->blend_x != nullptr, has_gn = p->gn_stats != nullptr;
+  if (g_dbg == 0 && p->act != HI3D_ACT_SILU && !(has_blend && !has_res)) {
+    if (p->act == HI3D_ACT_GEGLU) epi = (has_res || has_blend || has_gn) ? EPI_GENERIC : EPI_GEGLU;
+    else if (has_blend) epi = has_gn ? EPI_RESBLEND_GN : EPI_RESBLEND;
+    else if (has_res) epi = has_gn ? EPI_RES_GN : EPI_RES;
+    else epi = has_gn ? EPI_BIAS_GN : EPI_BIAS;
+  }
+  // 16 epilogue warps when the epilogue is the bound: short K (main loop of a tile shorter than its epilogue)
+  int ew = 8;
+  if ((epi == EPI_GEGLU || epi == EPI_BIAS) && (g_ew_mode == 16 || (g_ew_mode < 0 && p->K <= T5_EW16_MAX_K))) ew = 16;
+  const int extra_scr = (ew - T5_EPI_WARPS) * T5_SCR_BYTES;
   const int stage_bytes = T5_A_BYTES + (BN / ncta) * 128;
-  int stages = (T5_SMEM_BUDGET - gn_tab_bytes) / stage_bytes;
+  int stages = (T5_SMEM_BUDGET - gn_tab_bytes - extra_scr) / stage_bytes;
   if (stages > T5_MAX_STAGES) stages = T5_MAX_STAGES;
   if (stages < 2) { return hi3d_gemm(p, stream); }
   tp.BN = BN; tp.stages = stages;
@@ -845,17 +877,8 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   tp.dbg = g_dbg;
 
   const int smem_total = T5_SMEM_BUDGET + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + 1024;
-  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + T5_EPI_WARPS * T5_SCR_BYTES + gn_tab_bytes + 1024;
-  // epilogue specialisation
-  int epi = EPI_GENERIC;
-  const bool has_res = p->residual != nullptr, has_blend = p->blend_x != nullptr, has_gn = p->gn_stats != nullptr;
-  if (tp.dbg == 0 && p->act != HI3D_ACT_SILU && !(has_blend && !has_res)) {
-    if (p->act == HI3D_ACT_GEGLU) epi = (has_res || has_blend || has_gn) ? EPI_GENERIC : EPI_GEGLU;
-    else if (has_blend) epi = has_gn ? EPI_RESBLEND_GN : EPI_RESBLEND;
-    else if (has_res) epi = has_gn ? EPI_RES_GN : EPI_RES;
-    else epi = has_gn ? EPI_BIAS_GN : EPI_BIAS;
-  }
-  rc = launch_tc5(ncta, epi, tp, smem, smem_total, units, g_sm_count, st);
+  const int smem = stages * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048 + ew * T5_SCR_BYTES + gn_tab_bytes + 1024;
+  rc = launch_tc5(ncta, epi, ew, tp, smem, smem_total, units, g_sm_count, st);
   if (rc) return rc;
   return check_launch("hi3d_gemm_tc5");
 }

@@ -114,6 +114,9 @@ int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream);
  * HI3D_TC5_PAIR at first use), 0 = always single CTA, 1 = always CTA pairs.  Process-wide; the parity tests run every
  * geometry under both settings (no reference counterpart: the reference's cuDNN / cuBLAS pick their own tiles). */
 int hi3d_gemm_tc5_set_pair_mode(int mode);
+/* Test / tuning hook: epilogue warps of the specialised bias-only and GEGLU epilogues: -1 = automatic (16 when K <= 640, the
+ * GEMMs whose epilogue is the bound), 8 or 16 forced.  Process-wide; default from HI3D_TC5_EW. */
+int hi3d_gemm_tc5_set_epilogue_warps(int warps);
 
 /* Tiny channel counts (UNet input 8|17 ch, VAE image 3 ch / latent 4 ch) are zero-padded to 64 channels by
  * hi3d_sampler_pre / hi3d_nchw_to_nhwc so that the same engine serves input_blocks.0.0 (video_model.py:186-191),

@@ -13,6 +13,17 @@ from test_kernels_gpu import DEV, H, close, nhwc, rnd  # noqa: E402
 E = "tc5"
 
 
+@pytest.fixture(params=[-1, 8, 16], ids=["ew-auto", "ew8", "ew16"], autouse=True)
+def epilogue_warps(request):
+    """Every case runs with the automatic choice and with 8 / 16 epilogue warps forced (only the specialised bias-only and
+    GEGLU epilogues have a 16-warp build; everything else ignores the setting)."""
+    from hi3d_official_b200 import _native
+    lib = _native.load()
+    _native.check(lib.hi3d_gemm_tc5_set_epilogue_warps(request.param), "set_epilogue_warps")
+    yield request.param
+    _native.check(lib.hi3d_gemm_tc5_set_epilogue_warps(-1), "set_epilogue_warps")
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (300, 320, 320), (1000, 960, 640), (4096, 1280, 1280),
                                    (257, 2560, 320), (128, 64, 1024)])
 def test_tc5_plain(M, N, K):
