@@ -501,7 +501,7 @@ def main():
     ap.add_argument("--shard", default=None, choices=("videos", "frames"),
                     help="N > 1: 'frames' (default) = ONE video with its 16 frames sharded over the GPUs (strong scaling; K/V "
                          "+ halo + GN-statistics exchange per temporal layer); 'videos' = one video per GPU (weak scaling)")
-    ap.add_argument("--cpu-latent", type=int, default=64,
+    ap.add_argument("--cpu-latent", type=int, default=48,
                     help="latent size of the bounded cpu_baseline sample of the main arm (one real reference sampler step)")
     ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("HI3D_REF_BUDGET_S", 900)),
                     help="--impl reference: wall-clock budget for the real full-size sampler steps")

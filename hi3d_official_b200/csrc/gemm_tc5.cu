@@ -66,11 +66,9 @@ struct T5Params {
   float alpha;
   __half* out;
   int out_ld;
-  // GroupNorm statistics of the output (hi3d_gemm_params::gn_stats): per-CTA shared table [gn_spt samples][gn_upt units][2],
-  // flushed with global atomics once per tile
+  // GroupNorm statistics of the output (hi3d_gemm_params::gn_stats), added to the global table from the epilogue registers
   float* gn_stats;
   int gn_unit, gn_rows, gn_units, gn_nimg;   // channels per unit, GEMM-grid rows per image, units per image (N / unit), images
-  int gn_spt, gn_upt;                        // samples (images) a tile can touch, units an n-tile can touch
 };
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + MUFU error, far
@@ -195,7 +193,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
       reinterpret_cast<volatile uint32_t*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 32);
   float* sbias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64);   // [2][256]
   uint8_t* scratch = smem + STAGES * stage_bytes + 16 * T5_MAX_STAGES + 64 + 2048;                  // [EPI_WARPS][32 x 80]
-  float* gn_tab = reinterpret_cast<float*>(scratch + EW * T5_SCR_BYTES);                  // [gn_spt][gn_upt][2]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform role index
@@ -349,8 +346,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
       if (et < 256) sbias[et] = (p.bias != nullptr && et < BN && nb < p.N) ? __ldg(p.bias + nb) : 0.f;
     }
     const bool gn_on = kGn;
-    const int gn_tab_n = gn_on ? p.gn_spt * p.gn_upt * 2 : 0;
-    for (int i = et; i < gn_tab_n; i += 32 * EW) gn_tab[i] = 0.f;      // visible after the first bar.sync below
+
     for (int tile = unit0; tile < p.total_tiles; tile += nunits, at++) {
       const int mu = tile / p.n_tiles, nt = tile - mu * p.n_tiles;
       const int mt = mu * NCTA + (int)rank;
@@ -498,11 +494,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
           }
           __syncwarp();
           if (gn_on) {
-            // (sum, sumsq) of the values just stored (fp16-rounded: exactly what a statistics pass over the tensor sees).
-            // This lane: rows crow + 8 i, channels n + 8 cchk .. + 7.
-            const int u0 = n0 / p.gn_unit;                                  // first unit this n-tile can touch
-            if (gn_uniform) {
-              float2 s2[4], q2[4];                 // packed fp32 pairs: (sum, sumsq) of channels (2k, 2k+1) over this lane's rows
+            // (sum, sumsq) of the values just stored (fp16-rounded: exactly what a statistics pass over the tensor sees), per
+            // image and per unit of gn_unit channels, added to the global table with fire-and-forget RED.ADD.F32.
+            // This lane: rows crow + 8 i (i < 4), channels n + 8 cchk .. + 7.  (First version: a per-CTA shared-memory table
+            // flushed once per tile -- shared float atomics are compare-and-swap loops and the flush needed a 256-thread
+            // barrier per tile; it cost the GEMMs more than the statistics pass it replaced.)
+            const int cbase = n + cchk * 8;
+            if (gn_uniform && p.gn_unit >= 8) {
+              float2 s2[4], q2[4];                 // packed fp32: channel pairs (2k, 2k+1) summed over this lane's rows
 #pragma unroll
               for (int k = 0; k < 4; k++) s2[k] = q2[k] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -515,80 +514,51 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
                   q2[k] = __ffma2_rn(f, f, q2[k]);
                 }
               }
-              // per-warp reduction over the 8 row groups through the (now idle) transpose scratch: [lane][16 floats]
-              float* sc = reinterpret_cast<float*>(scr);
-              *reinterpret_cast<float4*>(sc + lane * 16) = make_float4(s2[0].x, s2[0].y, s2[1].x, s2[1].y);
-              *reinterpret_cast<float4*>(sc + lane * 16 + 4) = make_float4(s2[2].x, s2[2].y, s2[3].x, s2[3].y);
-              *reinterpret_cast<float4*>(sc + lane * 16 + 8) = make_float4(q2[0].x, q2[0].y, q2[1].x, q2[1].y);
-              *reinterpret_cast<float4*>(sc + lane * 16 + 12) = make_float4(q2[2].x, q2[2].y, q2[3].x, q2[3].y);
-              __syncwarp();
-              // lane j now owns channel n + j of the chunk
-              float S = 0.f, Q = 0.f;
-              const int jc = lane >> 3, je = lane & 7;
+              // 8 consecutive channels touch at most two units (gn_unit >= 8): split at the unit boundary
+              const int ua = cbase / p.gn_unit;
+              const int nb = (ua + 1) * p.gn_unit - cbase;          // channels of this lane that belong to unit ua (1..8)
+              float sA = 0.f, qA = 0.f, sT = 0.f, qT = 0.f;
 #pragma unroll
-              for (int r8 = 0; r8 < 8; r8++) {
-                S += sc[(r8 * 4 + jc) * 16 + je];
-                Q += sc[(r8 * 4 + jc) * 16 + 8 + je];
+              for (int k = 0; k < 4; k++) {
+                sT += s2[k].x + s2[k].y; qT += q2[k].x + q2[k].y;
+                sA += (2 * k < nb ? s2[k].x : 0.f) + (2 * k + 1 < nb ? s2[k].y : 0.f);
+                qA += (2 * k < nb ? q2[k].x : 0.f) + (2 * k + 1 < nb ? q2[k].y : 0.f);
               }
-              // Segmented sum over the lanes of one unit (consecutive channels), so that ONE lane per unit touches the table:
-              // shared-memory float atomics are compare-and-swap loops, and ten lanes hammering one address made the first
-              // version of this block cost more than the statistics pass it replaces.
-              const int uabs = (n + lane < p.N) ? (n + lane) / p.gn_unit : -1 - lane;     // distinct negatives: never merged
+              float sB = sT - sA, qB = qT - qA;
+              // sum over the 8 row groups (lanes with the same cchk: lane bits 2..4)
 #pragma unroll
-              for (int off = 1; off < 32; off <<= 1) {
-                const float so = __shfl_up_sync(0xffffffffu, S, off), qo = __shfl_up_sync(0xffffffffu, Q, off);
-                const int uo = __shfl_up_sync(0xffffffffu, uabs, off);
-                if (lane >= off && uo == uabs) { S += so; Q += qo; }
+              for (int off = 4; off < 32; off <<= 1) {
+                sA += __shfl_xor_sync(0xffffffffu, sA, off); qA += __shfl_xor_sync(0xffffffffu, qA, off);
+                sB += __shfl_xor_sync(0xffffffffu, sB, off); qB += __shfl_xor_sync(0xffffffffu, qB, off);
               }
-              const int unext = __shfl_down_sync(0xffffffffu, uabs, 1);
-              const bool seg_last = (lane == 31) || (unext != uabs);
-              const int smp = gn_wsmp;
-              if (seg_last && uabs >= 0 && smp >= 0 && smp < p.gn_spt) {
-                const int u = uabs - u0;
-                if (u >= 0 && u < p.gn_upt) {
-                  atomicAdd(&gn_tab[(smp * p.gn_upt + u) * 2], S);
-                  atomicAdd(&gn_tab[(smp * p.gn_upt + u) * 2 + 1], Q);
-                }
+              if (lane < 4 && gn_wsmp >= 0 && colok) {
+                float* dst = p.gn_stats + ((long long)(gn_s0 + gn_wsmp) * p.gn_units + ua) * 2;
+                atomicAdd(dst, sA); atomicAdd(dst + 1, qA);                       // results unused -> RED
+                if (nb < 8 && ua + 1 < p.gn_units) { atomicAdd(dst + 2, sB); atomicAdd(dst + 3, qB); }
               }
-              __syncwarp();
             } else {
-              // rows of several images inside one warp (images smaller than 32 pixels): per-element shared atomics
+              // tiny models (units narrower than 8 channels) or rows of several images inside one warp (images smaller
+              // than 32 pixels): one RED per stored pair -- only test-sized shapes come here
 #pragma unroll
               for (int i = 0; i < 4; i++) {
-                if (mrow[i] < 0 || !colok || gn_srow[i] < 0 || gn_srow[i] >= p.gn_spt) continue;
+                if (mrow[i] < 0 || !colok || gn_srow[i] < 0) continue;
+                float* row = p.gn_stats + (long long)(gn_s0 + gn_srow[i]) * p.gn_units * 2;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   const float2 f = __half22float2(w8s[i].h[k]);
-                  const int c0 = n + cchk * 8 + 2 * k;
-                  const int ua = c0 / p.gn_unit - u0, ub = (c0 + 1) / p.gn_unit - u0;
-                  if (ua >= 0 && ua < p.gn_upt) {
-                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ua) * 2], f.x);
-                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ua) * 2 + 1], f.x * f.x);
-                  }
-                  if (ub >= 0 && ub < p.gn_upt) {
-                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ub) * 2], f.y);
-                    atomicAdd(&gn_tab[(gn_srow[i] * p.gn_upt + ub) * 2 + 1], f.y * f.y);
+                  const int c0 = cbase + 2 * k;
+                  const int u0_ = c0 / p.gn_unit, u1_ = (c0 + 1) / p.gn_unit;
+                  if (u0_ == u1_) {
+                    atomicAdd(row + u0_ * 2, f.x + f.y); atomicAdd(row + u0_ * 2 + 1, f.x * f.x + f.y * f.y);
+                  } else {
+                    atomicAdd(row + u0_ * 2, f.x); atomicAdd(row + u0_ * 2 + 1, f.x * f.x);
+                    atomicAdd(row + u1_ * 2, f.y); atomicAdd(row + u1_ * 2 + 1, f.y * f.y);
                   }
                 }
               }
             }
           }
         }
-      }
-      if (gn_on) {
-        // every epilogue warp has added its chunks of this tile: flush the table (one global atomic per touched entry)
-        asm volatile("bar.sync 2, %0;\n" ::"n"(32 * EW) : "memory");
-        const int u0 = n0 / p.gn_unit;
-        for (int i = et; i < gn_tab_n; i += 32 * EW) {
-          const float v = gn_tab[i];
-          if (v != 0.f) {
-            const int which = i & 1, ent = i >> 1;
-            const int smp = ent / p.gn_upt + gn_s0, u = ent % p.gn_upt + u0;
-            if (smp < p.gn_nimg && u < p.gn_units) atomicAdd(p.gn_stats + ((long long)smp * p.gn_units + u) * 2 + which, v);
-            gn_tab[i] = 0.f;
-          }
-        }
-        // (the bar.sync 1 at the top of the next tile orders these zeroing stores before the next tile's atomics)
       }
       if (et < 256) sbias[(buf ^ 1) * 256 + et] = bnext;      // next tile's slice -> the buffer nobody reads until the next bar.sync
       // this warp is done reading the accumulator buffer
@@ -805,8 +775,8 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
       if (best < 0 || cost < best) { best = cost; BN = cand; }
     }
   }
-  // GroupNorm statistics in the epilogue: per-CTA table of (samples a tile can touch) x (units an n-tile can touch)
-  int gn_tab_bytes = 0;
+  // GroupNorm statistics in the epilogue
+  const int gn_tab_bytes = 0;
   if (p->gn_stats != nullptr) {
     const int hw = (p->mode == HI3D_ROWS_PLAIN) ? p->gn_rows : p->Ho * p->Wo;
     if (p->gn_unit <= 0 || (p->N % p->gn_unit) || p->gn_rows <= 0 || (p->M % p->gn_rows) || p->act == HI3D_ACT_GEGLU ||
@@ -816,10 +786,6 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     }
     tp.gn_stats = p->gn_stats; tp.gn_unit = p->gn_unit; tp.gn_rows = p->gn_rows;
     tp.gn_units = p->N / p->gn_unit; tp.gn_nimg = p->M / p->gn_rows;
-    tp.gn_spt = (p->mode == HI3D_ROWS_CONV2D) ? tp.tn : (p->mode == HI3D_ROWS_TEMPORAL) ? tp.th : (T5_BM / p->gn_rows + 2);
-    tp.gn_upt = BN / p->gn_unit + 2;
-    gn_tab_bytes = tp.gn_spt * tp.gn_upt * 2 * (int)sizeof(float);
-    if (gn_tab_bytes > 24 * 1024) return hi3d_gemm(p, stream);      // tiny images: the mma engine + a separate statistics pass
   }
   // epilogue specialisation and epilogue warp count (decided here: the scratch of 16 warps comes out of the stage budget)
   int epi = EPI_GENERIC;

@@ -126,19 +126,20 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   const int tid = threadIdx.x, n = blockIdx.y;
   if (stats1 != nullptr) {
     // statistics from the unit tables the producing GEMM epilogues accumulated (hi3d_gemm_params::gn_stats): group g of
-    // sample n = units [g cpg / unit, (g+1) cpg / unit) of the channel concat, over the `ips` images of the sample
-    if (tid < GN_GROUPS * 2) ssum[tid] = 0.f;
-    __syncthreads();
-    const int upg = cpg / unit, u1 = C1 / unit, u2 = C2 / unit;
-    const int items = GN_GROUPS * ips * upg;
-    for (int it = tid; it < items; it += blockDim.x) {
-      const int g = it / (ips * upg), rem = it - g * (ips * upg);
-      const int img = rem / upg, uu = rem - img * upg;
-      const int u = g * upg + uu;                                  // unit index within the concat
-      const long long im = (long long)n * ips + img;
-      const float* src = (u < u1) ? stats1 + (im * u1 + u) * 2 : stats2 + (im * u2 + (u - u1)) * 2;
-      atomicAdd(&ssum[2 * g], src[0]);
-      atomicAdd(&ssum[2 * g + 1], src[1]);
+    // sample n = units [g cpg / unit, (g+1) cpg / unit) of the channel concat, over the `ips` images of the sample.
+    // 64 threads, one per (group, sum | sumsq), each adding its <= ips * upg table entries in registers (independent loads).
+    if (tid < GN_GROUPS * 2) {
+      const int g = tid >> 1, which = tid & 1;
+      const int upg = cpg / unit, u1 = C1 / unit, u2 = C2 / unit;
+      float acc = 0.f;
+      for (int img = 0; img < ips; img++) {
+        const long long im = (long long)n * ips + img;
+        for (int uu = 0; uu < upg; uu++) {
+          const int u = g * upg + uu;
+          acc += (u < u1) ? __ldg(stats1 + (im * u1 + u) * 2 + which) : __ldg(stats2 + (im * u2 + (u - u1)) * 2 + which);
+        }
+      }
+      ssum[tid] = acc;
     }
     __syncthreads();
     fin = ssum - (long long)n * (GN_GROUPS * 2);                   // so that the indexing below reads ssum[...]
@@ -445,7 +446,9 @@ extern "C" int hi3d_groupnorm_apply_halo(const void* x1, int C1, const void* x2,
   const int RL = threads / CV;
   const long long min_rows = (long long)RL * GN_UNROLL;
   const long long max_by_rows = (rows_per_sample + min_rows - 1) / min_rows;
-  long long slabs = (GN_TARGET_CTAS + n_samples - 1) / n_samples;
+  // 2 CTAs per SM x 3 waves: a CTA lives ~4x longer than with the statistics kernels' grid, so its prologue (group statistics
+  // -> mean / rstd -> 16 coefficient registers) is amortised; measured 120 -> see profiles/r02 launch lists
+  long long slabs = (148 * 2 * 3 + n_samples - 1) / n_samples;
   if (slabs > max_by_rows) slabs = max_by_rows;
   if (slabs < 1) slabs = 1;
   long long rows_per_cta = (rows_per_sample + slabs - 1) / slabs;
