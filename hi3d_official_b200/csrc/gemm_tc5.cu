@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
             // flushed once per tile -- shared float atomics are compare-and-swap loops and the flush needed a 256-thread
             // barrier per tile; it cost the GEMMs more than the statistics pass it replaced.)
             const int cbase = n + cchk * 8;
-            if (gn_uniform && p.gn_unit >= 8) {
+            if (gn_uniform && p.gn_unit >= 4) {
               float2 s2[4], q2[4];                 // packed fp32: channel pairs (2k, 2k+1) summed over this lane's rows
 #pragma unroll
               for (int k = 0; k < 4; k++) s2[k] = q2[k] = make_float2(0.f, 0.f);
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
                   q2[k] = __ffma2_rn(f, f, q2[k]);
                 }
               }
-              // 8 consecutive channels touch at most two units (gn_unit >= 8): split at the unit boundary
+              // 8 consecutive channels (cbase is a multiple of 8) touch at most two units when gn_unit >= 4: split at the boundary
               const int ua = cbase / p.gn_unit;
               const int nb = (ua + 1) * p.gn_unit - cbase;          // channels of this lane that belong to unit ua (1..8)
               float sA = 0.f, qA = 0.f, sT = 0.f, qT = 0.f;
@@ -537,8 +537,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
                 if (nb < 8 && ua + 1 < p.gn_units) { atomicAdd(dst + 2, sB); atomicAdd(dst + 3, qB); }
               }
             } else {
-              // tiny models (units narrower than 8 channels) or rows of several images inside one warp (images smaller
-              // than 32 pixels): one RED per stored pair -- only test-sized shapes come here
+              // tiny models (units narrower than 4 channels: model_channels < 128) or rows of several images inside one warp
+              // (images smaller than 32 pixels): one RED per stored pair -- only test-sized shapes come here.  (The 128-channel
+              // VAE has 4-channel units: sending ITS 1024^2 tensors down this path cost 6 s per video in one measured build.)
 #pragma unroll
               for (int i = 0; i < 4; i++) {
                 if (mrow[i] < 0 || !colok || gn_srow[i] < 0) continue;

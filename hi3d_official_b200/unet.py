@@ -303,6 +303,7 @@ class _Plan:
                          and net.cfg.model_channels * max(net.cfg.channel_mult) // self.gn_unit <= 256)
         self._stats_floats = 0
         self.stats_arena = None
+        self._nvtx_open = False
         self.steps: List = []          # main per-step launch list (built lazily as (kind, builder) then baked)
         self._build: List = []         # deferred builders, run after the arena is materialised
         self._cond_build: List = []
@@ -337,8 +338,21 @@ class _Plan:
             dist.barrier(group=self.peer.pg)
 
     # ---- helpers -----------------------------------------------------------------------------------------------
-    def _gemm(self, lst, segs_fn, W, out: LazyBuf, M, **kw):
-        """Defer Gemm construction until buffers exist. segs_fn() -> list[SegSpec]; tensor kwargs may be LazyBuf."""
+    # Statistics in the epilogue are free where the main loop hides the epilogue (3x3 convs, wide temporal convs, K >= 1920 --
+    # the same threshold as the CTA-pair rule) and cost MORE than a separate statistics pass on the epilogue-bound short-K
+    # GEMMs (measured, profiles/r02_gn_epilogue_notes.txt: temporal conv C=320 +165 us per launch against 87 us for the
+    # pass): those keep the pass (hi3d_groupnorm_unit_stats, same table), still one launch less than r01's stats + finalize.
+    GN_FUSE_MIN_K = 1920
+
+    def _gemm(self, lst, segs_fn, W, out: LazyBuf, M, gn_defer: bool = False, **kw):
+        """Defer Gemm construction until buffers exist. segs_fn() -> list[SegSpec]; tensor kwargs may be LazyBuf.
+        gn_defer: the caller adds the separate statistics pass itself (several launches fill one tensor)."""
+        post = None
+        if kw.get("gn_stats") is not None and W.shape[1] < self.GN_FUSE_MIN_K:
+            st, unit, rows = kw.pop("gn_stats"), kw.pop("gn_unit"), kw.pop("gn_rows")
+            if not gn_defer:
+                post = lambda: (lambda: ops.groupnorm_unit_stats(out.t, st.n_img, (out.rows // st.n_img), unit, st.t))
+
         def build():
             k2 = {}
             for k, v in kw.items():
@@ -347,6 +361,21 @@ class _Plan:
             self.flops += g.flops if lst is self._build else 0.0
             return g
         lst.append(build)
+        if post is not None:
+            fn = post()
+            fn.kind, fn.bytes = "groupnorm", 2.0 * out.rows * out.cols
+            lst.append(lambda fn=fn: fn)
+
+    def _mark(self, name: str):
+        """HI3D_NVTX=1: an NVTX range per layer of the launch plan (block name as in the state dict), so that ncu / nsys
+        captures can be filtered and read by layer (`ncu --nvtx --nvtx-include "input_blocks.1.1.*/"`).  Host-side marker
+        calls only; not part of CUDA-graph replays (profile with HI3D_CUDA_GRAPH=0)."""
+        if os.environ.get("HI3D_NVTX", "0") == "1":
+            def m(name=name):
+                torch.cuda.nvtx.range_pop() if self._nvtx_open else None
+                torch.cuda.nvtx.range_push(name)
+                self._nvtx_open = True
+            self._call(self._build, m, kind="marker")
 
     def _stats(self, n_img: int, C: int) -> Optional[StatsBuf]:
         if not self.gn_fused:
@@ -494,15 +523,26 @@ class _Plan:
         parity, b = wb
         n_img = self.N if n_img is None else n_img
         M = n_img * h * w
+        fused = True
         for (py, px), (Wt, shifts) in parity.items():
+            fused = Wt.shape[1] >= self.GN_FUSE_MIN_K
             self._gemm(lst, lambda shifts=shifts: [ops.SegSpec(src.t, dy=sy, dx=sx) for sy, sx in shifts], Wt, out, M,
-                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=b, **kw)
+                       mode=ops.ROWS_CONV2D, geom=dict(Ho=h, Wo=w, Hs=h, Ws=w, out_up=1, out_py=py, out_px=px), bias=b,
+                       gn_defer=True, **kw)
+        if kw.get("gn_stats") is not None and not fused:       # one statistics pass over the tensor the four launches filled
+            st, unit = kw["gn_stats"], kw["gn_unit"]
+            self._call(lst, lambda: ops.groupnorm_unit_stats(out.t, st.n_img, out.rows // st.n_img, unit, st.t),
+                       kind="groupnorm", bytes=2.0 * out.rows * out.cols)
 
     def _emb_slice(self, q):
         off, n = self.P["emb_off"][q]
         return self.emb_all[:, off:off + n]
 
     def _resblock(self, L: Layer, srcs: List[tuple], out: LazyBuf, out_stats, h: int, w: int):
+        self._mark(L.name + "VideoResBlock")
+        return self._resblock_impl(L, srcs, out, out_stats, h, w)
+
+    def _resblock_impl(self, L: Layer, srcs: List[tuple], out: LazyBuf, out_stats, h: int, w: int):
         """VideoResBlock (video_model.py:62-81) = spatial ResBlock (openaimodel.py:328-354) + temporal ResBlock
         (dims=3, kernel (3,1,1), GroupNorm over (C/32, T, H, W)) + AlphaBlender, as 4 GN launches + 4 GEMMs.
         srcs = [(buffer, C, h, w, stats), ...] (two entries = the skip concat); every GEMM whose output feeds a GroupNorm
@@ -594,6 +634,10 @@ class _Plan:
                        bias=P[q + wkey][1], **extra)
 
     def _transformer(self, L: Layer, xin: tuple, out: LazyBuf, out_stats, h: int, w: int):
+        self._mark(L.name + "SpatialVideoTransformer")
+        return self._transformer_impl(L, xin, out, out_stats, h, w)
+
+    def _transformer_impl(self, L: Layer, xin: tuple, out: LazyBuf, out_stats, h: int, w: int):
         """SpatialVideoTransformer.forward (video_attention.py:230-301), see module docstring for the folds."""
         P, A, bl, cl, N, T, B = self.P, self.arena, self._build, self._cond_build, self.N, self.T, self.B
         x = xin[0]
@@ -714,6 +758,9 @@ class _Plan:
     def run(self):
         for s in self.steps:
             s()
+        if self._nvtx_open:
+            torch.cuda.nvtx.range_pop()
+            self._nvtx_open = False
 
     def launches_per_step(self) -> int:
         from . import _native
