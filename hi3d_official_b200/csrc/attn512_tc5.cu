@@ -5,8 +5,10 @@
 // none for the scores.  So a CTA owns 128 queries and HALF of the value dimension (256 columns): grid (L/128, 2, images);
 // both halves compute the full S = Q K^T (contraction over 512) -- 1.5x the minimal tensor work, on a block that is ~1 % of
 // a video.  TMEM: S [0,128) fp32, P [128,192) packed fp16, O [192,448) fp32.
-//   S = sum over eight 64-wide chunks c of Q_c K_c^T: Q_c and K_c stream through a 4-stage TMA ring (32 KB per stage; Q is
-//       re-fetched per key tile from L2, cheaper than parking 128 KB of it in shared memory next to K and V),
+//   S = sum over eight 64-wide chunks c of Q_c K_c^T: the 128 x 512 query tile (128 KB) stays RESIDENT in shared memory, the
+//       K chunks and the four 64-column V chunks of a key tile stream through one 4-stage ring of 16 KB tiles in the order
+//       the MMA warp consumes them (K(0) x8, V(0) x4, K(1) x8, ...): 192 KB from L2 per key tile and CTA.  (A first version
+//       re-fetched Q per key tile: 320 KB per tile, L2-bandwidth bound at ~3x the tensor time.)
 //   softmax: four warps, one thread per query row and 128 keys per tile in four 32-column sweeps, lazy reference maximum as
 //       in the d = 64 kernel (P <= 2^8; on overflow the row's accumulator is rescaled in TMEM and P redone from S, which P
 //       does not alias here),
@@ -25,7 +27,7 @@ constexpr int F5_BM = 128, F5_BN = 128, F5_D = 512, F5_DV = 256;
 constexpr int F5_THREADS = 192;                    // warp 0 producer, warp 1 MMA, warps 2..5 softmax
 constexpr int F5_STAGES = 4;
 constexpr int F5_TILE = 128 * 128;                 // 128 rows x 64 fp16
-constexpr int F5_SMEM = F5_STAGES * 2 * F5_TILE + 4 * F5_TILE + 512 + 1024;
+constexpr int F5_SMEM = 8 * F5_TILE + F5_STAGES * F5_TILE + 512 + 1024;
 
 struct Fa512Params {
   CUtensorMap qkv_map;     // [rows, 1536] fp16 (q | k | v), box {64, 128}
@@ -45,14 +47,13 @@ __global__ void __launch_bounds__(F5_THREADS, 1) fmha512_tc5_kernel(const __grid
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sQK = base;                                   // stage s: Q_c at s*2T, K_c at s*2T + T
-  const uint32_t sV = base + F5_STAGES * 2 * F5_TILE;          // 4 chunks [128 keys x 64 columns]
-  const uint32_t bar0 = sV + 4 * F5_TILE;
-  const uint32_t bar_qk_full = bar0;                           // [STAGES]
-  const uint32_t bar_qk_empty = bar0 + 8 * F5_STAGES;          // [STAGES]
-  const uint32_t bar_v_full = bar_qk_empty + 8 * F5_STAGES;
-  const uint32_t bar_v_empty = bar_v_full + 8;
-  const uint32_t bar_s_full = bar_v_empty + 8;
+  const uint32_t sQ = base;                                    // 8 chunks [128 queries x 64], resident
+  const uint32_t sR = base + 8 * F5_TILE;                      // ring: F5_STAGES tiles [128 keys x 64] (K chunks, then V chunks)
+  const uint32_t bar0 = sR + F5_STAGES * F5_TILE;
+  const uint32_t bar_full = bar0;                              // [STAGES]
+  const uint32_t bar_empty = bar0 + 8 * F5_STAGES;             // [STAGES]
+  const uint32_t bar_q = bar_empty + 8 * F5_STAGES;
+  const uint32_t bar_s_full = bar_q + 8;
   const uint32_t bar_p_full = bar_s_full + 8;                  // 4 arrivals
   const uint32_t bar_o_full = bar_p_full + 8;
   const uint32_t tmem_slot = bar_o_full + 16;
@@ -66,9 +67,8 @@ __global__ void __launch_bounds__(F5_THREADS, 1) fmha512_tc5_kernel(const __grid
   const int nkv = p.L / F5_BN;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < F5_STAGES; s++) { mbar_init(bar_qk_full + 8 * s, 1); mbar_init(bar_qk_empty + 8 * s, 1); }
-    mbar_init(bar_v_full, 1);
-    mbar_init(bar_v_empty, 1);
+    for (int s = 0; s < F5_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_q, 1);
     mbar_init(bar_s_full, 1);
     mbar_init(bar_p_full, 4);
     mbar_init(bar_o_full, 1);
@@ -86,27 +86,24 @@ __global__ void __launch_bounds__(F5_THREADS, 1) fmha512_tc5_kernel(const __grid
 
   if (warp == 0) {
     // ======================= TMA producer =======================
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, 8 * F5_TILE);
+      for (int c = 0; c < 8; c++) tma_load_2d(sQ + c * F5_TILE, &p.qkv_map, bar_q, c * 64, row0 + q0);
+    }
+    __syncwarp();
     uint32_t s = 0, ph = 0;
     for (int j = 0; j < nkv; j++) {
-      for (int c = 0; c < F5_D / 64; c++) {
-        mbar_wait(bar_qk_empty + 8 * s, ph ^ 1);
+      for (int c = 0; c < 12; c++) {           // 8 K chunks, then this CTA's 4 V chunks
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
         if (elect_one()) {
-          const uint32_t full = bar_qk_full + 8 * s;
-          mbar_expect_tx(full, 2 * F5_TILE);
-          tma_load_2d(sQK + s * 2 * F5_TILE, &p.qkv_map, full, c * 64, row0 + q0);
-          tma_load_2d(sQK + s * 2 * F5_TILE + F5_TILE, &p.qkv_map, full, F5_D + c * 64, row0 + j * F5_BN);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, F5_TILE);
+          const int col = (c < 8) ? (F5_D + c * 64) : (2 * F5_D + dvh * F5_DV + (c - 8) * 64);
+          tma_load_2d(sR + s * F5_TILE, &p.qkv_map, full, col, row0 + j * F5_BN);
         }
         __syncwarp();
         if (++s == F5_STAGES) { s = 0; ph ^= 1; }
       }
-      // this CTA's half of V for tile j, once P V(j-1) has retired
-      mbar_wait(bar_v_empty, (j & 1) ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(bar_v_full, 4 * F5_TILE);
-        for (int vc = 0; vc < 4; vc++)
-          tma_load_2d(sV + vc * F5_TILE, &p.qkv_map, bar_v_full, 2 * F5_D + dvh * F5_DV + vc * 64, row0 + j * F5_BN);
-      }
-      __syncwarp();
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
@@ -115,13 +112,13 @@ __global__ void __launch_bounds__(F5_THREADS, 1) fmha512_tc5_kernel(const __grid
     uint32_t s = 0, ph = 0;
     auto issue_s = [&]() {     // S = sum_c Q_c K_c^T  (whole warp walks the ring, one elected lane issues)
       for (int c = 0; c < F5_D / 64; c++) {
-        mbar_wait(bar_qk_full + 8 * s, ph);
+        mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t qd = umma_desc_sw128(sQK + s * 2 * F5_TILE), kd = umma_desc_sw128(sQK + s * 2 * F5_TILE + F5_TILE);
+          const uint64_t qd = umma_desc_sw128(sQ + c * F5_TILE), kd = umma_desc_sw128(sR + s * F5_TILE);
 #pragma unroll
           for (int k = 0; k < 4; k++) tc_mma_f16(tS0, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, (c | k) ? 1u : 0u);
-          tc_commit(bar_qk_empty + 8 * s);
+          tc_commit(bar_empty + 8 * s);
         }
         __syncwarp();
         if (++s == F5_STAGES) { s = 0; ph ^= 1; }
@@ -129,23 +126,24 @@ __global__ void __launch_bounds__(F5_THREADS, 1) fmha512_tc5_kernel(const __grid
       if (elect_one()) tc_commit(bar_s_full);
       __syncwarp();
     };
+    mbar_wait(bar_q, 0);
     issue_s();
     for (int j = 0; j < nkv; j++) {
       mbar_wait(bar_p_full, j & 1);              // P(j) in TMEM, every softmax warp done with S(j)
-      mbar_wait(bar_v_full, j & 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int vc = 0; vc < 4; vc++) {
-          const uint64_t vd = umma_desc_sw128_mn(sV + vc * F5_TILE);
+      for (int vc = 0; vc < 4; vc++) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t vd = umma_desc_sw128_mn(sR + s * F5_TILE);
 #pragma unroll
           for (int k = 0; k < 8; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
             tc_mma_f16_ts(tO0 + 64u * vc, tP0 + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, (j | k) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * s);
+          if (vc == 3) tc_commit(bar_o_full);
         }
-        tc_commit(bar_o_full);
-        tc_commit(bar_v_empty);
+        __syncwarp();
+        if (++s == F5_STAGES) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
       if (j + 1 < nkv) issue_s();                // behind P V(j) on the tensor pipe: P(j) is consumed before softmax(j+1) starts
     }
   } else {

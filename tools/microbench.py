@@ -122,6 +122,13 @@ def main():
             report(f"temporal attention S={L} heads={heads}",
                    timeit(lambda: ops.temporal_attention_d64(qkv, 2, T, L, heads, out), once=args.once), 4.0 * N * L * T * C,
                    8.0 * M * C)
+    if args.only in ("", "vae", "attn"):
+        for L in ((hw * 8 // 8) ** 2 // 1,):          # (H/8)^2 of the stage's image size: 4096 (512^2) / 16384 (1024^2)
+            for n_img in (1, 4):
+                qkv = rnd(n_img * L, 1536)
+                out = torch.empty(n_img * L, 512, dtype=H, device=DEV)
+                report(f"VAE attention d=512 flash L={L} n={n_img}",
+                       timeit(lambda: ops.attention_d512(qkv, n_img, L, out), once=args.once), 4.0 * n_img * L * L * 512)
     if args.only in ("", "norm"):
         for ds, C in ((1, 320), (2, 640), (4, 1280), (1, 640)):
             h = hw // ds
