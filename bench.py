@@ -503,7 +503,7 @@ def main():
                          "+ halo + GN-statistics exchange per temporal layer); 'videos' = one video per GPU (weak scaling)")
     ap.add_argument("--cpu-latent", type=int, default=48,
                     help="latent size of the bounded cpu_baseline sample of the main arm (one real reference sampler step)")
-    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("HI3D_REF_BUDGET_S", 900)),
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("HI3D_REF_BUDGET_S", 300)),
                     help="--impl reference: wall-clock budget for the real full-size sampler steps")
     ap.add_argument("--no-stage1", action="store_true", help="skip the extra stage-1 measurement of the N=1 stage-2 run")
     ap.add_argument("--ref-latent", type=int, default=0,

@@ -17,7 +17,7 @@ for X in $S; do
     timeout 1800 python bench.py --steps 3 --warmup 3 > ${P}_bench_stage2.json 2> ${P}_bench_stage2.err; echo "bench rc=$?"
     cut -c1-300 ${P}_bench_stage2.json ;;
   ref)
-    timeout 1500 python bench.py --impl reference --steps 1 --warmup 1 --ref-budget-s 650 > ${P}_bench_reference_arm.json 2> ${P}_bench_reference_arm.err; echo "ref rc=$?"
+    timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > ${P}_bench_reference_arm.json 2> ${P}_bench_reference_arm.err; echo "ref rc=$?"
     cut -c1-900 ${P}_bench_reference_arm.json ;;
   ncu)
     timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${P}_launches_s2.csv python tools/one_step.py --stage 2 > ${P}_ncu_list.log 2>&1; echo "ncu list rc=$?"
