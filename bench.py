@@ -138,9 +138,14 @@ def shard_frames(t: dict, rank: int, world: int) -> dict:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
 # (not measurable live): mean over the 10 hi3d_gemm_tc5 launches of input block 1 (64x64 level: conv3x3, temporal conv,
 # proj_in, qkv, attention out, GEGLU, ff2 ...), each 84-420 MB algorithmic.  Stage 2 was not captured.
-NCU_GEMM_TRAFFIC = {1: 292.8e6}
-NCU_GEMM_TRAFFIC_NOTE = ("bytes per launch, mean of the 10 top-level GEMM launches in profiles/r01_ncu_full_stage1_final.txt "
-                         "(ncu --set full, caches flushed per pass); `achieved` averages all 300 GEMM launches of a forward")
+NCU_GEMM_TRAFFIC = {1: 292.8e6, 2: 1163.7e6}
+NCU_GEMM_TRAFFIC_NOTE = {
+    1: ("bytes per launch, mean of the 10 top-level GEMM launches in profiles/r01_ncu_full_stage1_final.txt "
+        "(ncu --set full, caches flushed per pass); `achieved` averages all 300 GEMM launches of a forward"),
+    2: ("dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 13 top-level (128x128 latent) GEMM launches in "
+        "profiles/r02_ncu_full_stage2.txt (ncu --set full, caches flushed per pass; algorithmic bytes of the same launches: "
+        "A + output + residual = 0.67-1.7 GB); `achieved` averages all 300 GEMM launches of a forward"),
+}
 
 
 def kernel_breakdown(model, stage: int, dev_t, peaks):
@@ -207,7 +212,7 @@ def kernel_breakdown(model, stage: int, dev_t, peaks):
         roof = dict(bound="tensor", kernel="hi3d_gemm (implicit-GEMM conv/linear, all launches of one UNet step)",
                     achieved=round(ach, 1), peak=peaks["tf_sust"], unit="TFLOP/s", frac=round(ach / peaks["tf_sust"], 4),
                     peak_source=f"{peaks['src']} bf16_tflops_sustained", traffic=NCU_GEMM_TRAFFIC.get(stage),
-                    traffic_note=NCU_GEMM_TRAFFIC_NOTE if stage in NCU_GEMM_TRAFFIC else None,
+                    traffic_note=NCU_GEMM_TRAFFIC_NOTE.get(stage),
                     flops_per_step=g["flops"], avg_launch_ms=round(g["ms"] / g["launches"], 4))
     out["sum_of_launches_ms"] = round(tot, 3)
     return out, roof, fwd_ms

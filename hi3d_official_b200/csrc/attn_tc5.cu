@@ -90,6 +90,26 @@ HI3D_DEVINL void softmax_exp32(const uint32_t (&cur)[32], float c, float nmoff, 
   }
 }
 
+// The same for 16 scores -> 8 packed half2 at pk[OFF .. OFF + 8) (register-lean chunks of the split kernel's MODE 2 loop).
+template <int EMU, int OFF>
+HI3D_DEVINL void softmax_exp16(const uint32_t (&cur)[16], float c, float nmoff, uint32_t (&pk)[16], float2 (&rs)[2]) {
+  const float2 c2 = make_float2(c, c), m2 = make_float2(nmoff, nmoff);
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    const float2 x = __ffma2_rn(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), c2, m2);
+    float2 pe;
+    if (((i >> 1) & 3) < EMU) pe = ex2_emulated2(x);
+    else pe = make_float2(ex2_approx_ftz(x.x), ex2_approx_ftz(x.y));
+    rs[(i >> 1) & 1] = __fadd2_rn(rs[(i >> 1) & 1], pe);
+    pk[OFF + (i >> 1)] = pack_half2(pe.x, pe.y);
+  }
+}
+HI3D_DEVINL void rowmax16(const uint32_t (&cur)[16], float (&mxa)[4]) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2)
+    mxa[(i >> 1) & 3] = fmaxf(mxa[(i >> 1) & 3], fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
+}
+
 struct FaParams {
   CUtensorMap qkv_map;     // 2-D view of the packed [rows, 3C] matrix, box {64, 128}
   int L, C, heads;
@@ -353,7 +373,11 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
 //   columns.  With two CTAs per SM this gives four pipelines per SM that drift out of phase, so the MUFU pipe (the bound:
 //   16384 ex2 per tile) always has a half-tile to work on.
 // =====================================================================================================================
-template <int EMU>
+// MODE bit 0: the MMA warp serves whichever half has its P ready first (polls both barriers) instead of half 0, half 1.
+// MODE bit 1: register-lean softmax loop -- the scores are read in four 16-column chunks and P is only stored once the
+//   whole half-tile has been accepted, so S stays intact in TMEM for the (rare) redo, which re-reads it in two passes;
+//   ~16 registers less at the peak, which is what lets the FMA-pipe exponentials (EMU) fit without spilling.
+template <int EMU, int MODE>
 __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -439,8 +463,24 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     for (int j = 0; j < nkv; j++) {
       const int s = j % FA_STAGES;
       const int s1 = (j + 1) % FA_STAGES;
-      for (int hh = 0; hh < 2; hh++) {
-        mbar_wait(bar_p_full + 8 * hh, j & 1);                  // P_h(j) is in TMEM (aliasing S_h)
+      uint32_t pend = 3u;                                       // halves of tile j not yet served (warp-uniform)
+      uint32_t polls = 0;
+      while (pend) {
+        int hh;
+        if constexpr (MODE & 1) {
+          // whichever half is ready: every lane must have seen the phase complete itself (uniform decision)
+          const bool r0 = (pend & 1u) && __all_sync(0xffffffffu, mbar_test(bar_p_full, j & 1));
+          const bool r1 = !r0 && (pend & 2u) && __all_sync(0xffffffffu, mbar_test(bar_p_full + 8, j & 1));
+          if (!r0 && !r1) {
+            if ((++polls & 0xfffffu) == 0u) mbar_wait(bar_p_full + ((pend & 1u) ? 0 : 8), j & 1);   // falls into the watchdog wait
+            continue;
+          }
+          hh = r0 ? 0 : 1;
+        } else {
+          hh = (pend & 1u) ? 0 : 1;
+          mbar_wait(bar_p_full + 8 * hh, j & 1);                // P_h(j) is in TMEM (aliasing S_h)
+        }
+        pend &= ~(1u << hh);
         if (j + 1 < nkv) mbar_wait(bar_kv_full + 8 * s1, ((j + 1) / FA_STAGES) & 1);
         tc_fence_after();
         if (elect_one()) {
@@ -449,7 +489,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
           for (int k = 0; k < 4; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
             tc_mma_f16_ts(tO0 + 64u * hh, tS0 + 64u * hh + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, (j | k) ? 1u : 0u);
           tc_commit(bar_o_full + 8 * hh);
-          if (hh == 1) tc_commit(bar_kv_empty + 8 * s);         // both halves of tile j have been issued
+          if (pend == 0u) tc_commit(bar_kv_empty + 8 * s);      // both halves of tile j have been issued
           if (j + 1 < nkv) {                                    // in order behind P_h V_h(j): overwrites the aliased columns
             const uint64_t kd = umma_desc_sw128(sKV + s1 * 2 * FA_TILE_BYTES + hh * 8192);
 #pragma unroll
@@ -470,6 +510,97 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     const uint32_t tS = tS0 + lane_off + 64u * hf, tO = tO0 + lane_off + 64u * hf;
     const uint32_t b_s = bar_s_full + 8 * hf, b_p = bar_p_full + 8 * hf, b_o = bar_o_full + 8 * hf;
     float m_ref = -INFINITY, l_run = 0.f;        // reference maximum and row sum of THIS half
+    if constexpr (MODE & 2) {
+      for (int j = 0; j < nkv; j++) {
+        mbar_wait(b_s, j & 1);
+        tc_fence_after();
+        uint32_t a[16], b[16], pka[16], pkb[16];
+        float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        bool redo = (j == 0);
+        if (!redo) {
+          // optimistic pass against the current reference; nothing is stored until the half-tile has been accepted
+          const float nmoff = -(m_ref * c);
+          tmem_ld16(tS, a);
+          tmem_ld_wait16(a);
+          tmem_ld16(tS + 16, b);
+          softmax_exp16<EMU, 0>(a, c, nmoff, pka, rs);
+          tmem_ld_wait16(b);
+          tmem_ld16(tS + 32, a);
+          softmax_exp16<EMU, 8>(b, c, nmoff, pka, rs);
+          tmem_ld_wait16(a);
+          tmem_ld16(tS + 48, b);
+          softmax_exp16<EMU, 0>(a, c, nmoff, pkb, rs);
+          tmem_ld_wait16(b);
+          softmax_exp16<EMU, 8>(b, c, nmoff, pkb, rs);
+          // Accept the half-tile if its row sum stays below 2^12: then every P <= 2^12 (no fp16 overflow; the relative
+          // precision of P does not depend on its scale), and a sum is what the loop computes anyway -- no maximum over the
+          // scores at all in the common path (33 FMNMX3 less per 64 scores).  inf / NaN sums fail the test too.
+          const float tsum = (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
+          redo = __any_sync(0xffffffffu, !(tsum <= 4096.0f)) != 0;
+          if (!redo) {
+            l_run += tsum;
+            tmem_st16(tS, pka);
+            tmem_st16(tS + 16, pkb);
+          }
+        }
+        if (redo) {
+          // the reference moves (always on the first tile).  S is intact in TMEM: pass 1 = row maximum, pass 2 = P.
+          float mxa[4] = {m_ref, m_ref, m_ref, m_ref};
+          {
+            tmem_ld16(tS, a);
+            tmem_ld_wait16(a);
+            tmem_ld16(tS + 16, b);
+            rowmax16(a, mxa);
+            tmem_ld_wait16(b);
+            tmem_ld16(tS + 32, a);
+            rowmax16(b, mxa);
+            tmem_ld_wait16(a);
+            tmem_ld16(tS + 48, b);
+            rowmax16(a, mxa);
+            tmem_ld_wait16(b);
+            rowmax16(b, mxa);
+          }
+          const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));     // >= m_ref
+          const float corr = ex2_approx_ftz((m_ref - mx) * c);                        // m_ref = -inf on the first tile -> 0
+          m_ref = mx;
+          if (j > 0) {
+            mbar_wait(b_o, (j - 1) & 1);            // P_h V_h(j-1) has retired: O_h is complete up to tile j-1
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 4; cc++) {
+              tmem_ld16(tO + 16 * cc, a);
+              tmem_ld_wait16(a);
+#pragma unroll
+              for (int i = 0; i < 16; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) * corr);
+              tmem_st16(tO + 16 * cc, a);
+            }
+          }
+          rs[0] = make_float2(0.f, 0.f);
+          rs[1] = make_float2(0.f, 0.f);
+          const float nmoff = -(mx * c);
+          // P chunk k (8 packed columns) lands on score columns [8k, 8k + 8): always columns that were read before
+          tmem_ld16(tS, a);
+          tmem_ld_wait16(a);
+          tmem_ld16(tS + 16, b);
+          softmax_exp16<0, 0>(a, c, nmoff, pka, rs);
+          tmem_ld_wait16(b);
+          tmem_ld16(tS + 32, a);
+          softmax_exp16<0, 8>(b, c, nmoff, pka, rs);
+          tmem_ld_wait16(a);
+          tmem_ld16(tS + 48, b);
+          softmax_exp16<0, 0>(a, c, nmoff, pkb, rs);
+          tmem_ld_wait16(b);
+          softmax_exp16<0, 8>(b, c, nmoff, pkb, rs);
+          tmem_st16(tS, pka);
+          tmem_st16(tS + 16, pkb);
+          l_run = l_run * corr + (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_p);
+      }
+    } else
     for (int j = 0; j < nkv; j++) {
       mbar_wait(b_s, j & 1);
       tc_fence_after();
@@ -593,36 +724,50 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
 
 using namespace hi3d;
 
-// fraction of the exponentials computed on the FMA pipe: EMU / 4 (0, 1 or 2); -1 = unread (HI3D_FMHA_EMU, else default)
+// fraction of the exponentials computed on the FMA pipe: EMU / 4 (0 .. 4; 3 and 4 only in the lean split kernels);
+// -1 = unread (HI3D_FMHA_EMU, else default)
 static int g_fmha_emu = -1;
 constexpr int FA_EMU_DEFAULT = 0;     // measured (profiles/r02_microbench_attn.txt): 1/4 helps the shared-row kernel (+2..18 %), hurts the split one
 
 extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
-  if (quarters < 0 || quarters > 2) { set_error("hi3d_attention_tc5_set_exp_emulation: 0, 1 or 2 (quarters of the exponentials)"); return -2; }
+  if (quarters < 0 || quarters > 4) { set_error("hi3d_attention_tc5_set_exp_emulation: 0 .. 4 (quarters of the exponentials)"); return -2; }
   g_fmha_emu = quarters;
   return 0;
 }
 
-static int g_fmha_variant = -1;    // 0 = shared-row kernel, 1 = split half-tile pipelines; -1 = unread (HI3D_FMHA_VARIANT)
+// 0 = shared-row kernel, 1 = split half-tile pipelines, 2 = split + register-lean softmax loop, 3 = 2 + the MMA warp serves
+// whichever half is ready; -1 = unread (HI3D_FMHA_VARIANT)
+static int g_fmha_variant = -1;
 constexpr int FA_VARIANT_DEFAULT = 1;  // split pipelines: 783 vs 744 TFLOP/s at L = 16384, 768 vs 726 at L = 4096 x 10 heads
 
 extern "C" int hi3d_attention_tc5_set_variant(int variant) {
-  if (variant < 0 || variant > 1) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows) or 1 (split pipelines)"); return -2; }
+  if (variant < 0 || variant > 3) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows), 1 (split), 2 (split, lean), 3 (split, lean, any-order)"); return -2; }
   g_fmha_variant = variant;
   return 0;
 }
 
+template <int EMU, int MODE>
+static int launch_fmha_split(const FaParams& fp, dim3 grid, cudaStream_t st) {
+  static bool attr_done[HI3D_MAX_DEVICES];
+  if (ensure_dyn_smem(fmha_tc5_split_kernel<EMU, MODE>, FA_SMEM, attr_done, "hi3d_attention_d64_tc5")) return -1;
+  fmha_tc5_split_kernel<EMU, MODE><<<grid, FA_THREADS, FA_SMEM, st>>>(fp);
+  return check_launch("hi3d_attention_d64_tc5");
+}
+
 template <int EMU>
 static int launch_fmha(const FaParams& fp, dim3 grid, cudaStream_t st) {
-  static bool attr_done[HI3D_MAX_DEVICES], attr_done_split[HI3D_MAX_DEVICES];
-  if (g_fmha_variant == 1) {
-    if (ensure_dyn_smem(fmha_tc5_split_kernel<EMU>, FA_SMEM, attr_done_split, "hi3d_attention_d64_tc5")) return -1;
-    fmha_tc5_split_kernel<EMU><<<grid, FA_THREADS, FA_SMEM, st>>>(fp);
-  } else {
+  static bool attr_done[HI3D_MAX_DEVICES];
+  if (g_fmha_variant == 3) return launch_fmha_split<EMU, 3>(fp, grid, st);
+  if (g_fmha_variant == 2) return launch_fmha_split<EMU, 2>(fp, grid, st);
+  if constexpr (EMU <= 2) {
+    if (g_fmha_variant == 1) return launch_fmha_split<EMU, 0>(fp, grid, st);
     if (ensure_dyn_smem(fmha_tc5_kernel<EMU>, FA_SMEM, attr_done, "hi3d_attention_d64_tc5")) return -1;
     fmha_tc5_kernel<EMU><<<grid, FA_THREADS, FA_SMEM, st>>>(fp);
+    return check_launch("hi3d_attention_d64_tc5");
+  } else {
+    set_error("hi3d_attention_d64_tc5: exp emulation %d/4 needs variant 2 or 3", EMU);
+    return -2;
   }
-  return check_launch("hi3d_attention_d64_tc5");
 }
 
 extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream) {
@@ -647,17 +792,19 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   if (g_fmha_emu < 0) {
     const char* e = getenv("HI3D_FMHA_EMU");
     g_fmha_emu = e ? atoi(e) : FA_EMU_DEFAULT;
-    if (g_fmha_emu < 0 || g_fmha_emu > 2) g_fmha_emu = FA_EMU_DEFAULT;
+    if (g_fmha_emu < 0 || g_fmha_emu > 4) g_fmha_emu = FA_EMU_DEFAULT;
   }
   if (g_fmha_variant < 0) {
     const char* e = getenv("HI3D_FMHA_VARIANT");
     g_fmha_variant = e ? atoi(e) : FA_VARIANT_DEFAULT;
-    if (g_fmha_variant < 0 || g_fmha_variant > 1) g_fmha_variant = FA_VARIANT_DEFAULT;
+    if (g_fmha_variant < 0 || g_fmha_variant > 3) g_fmha_variant = FA_VARIANT_DEFAULT;
   }
   dim3 grid(L / FA_BM, heads, n_img);
   switch (g_fmha_emu) {
     case 1: return launch_fmha<1>(fp, grid, (cudaStream_t)stream);
     case 2: return launch_fmha<2>(fp, grid, (cudaStream_t)stream);
+    case 3: return launch_fmha<3>(fp, grid, (cudaStream_t)stream);
+    case 4: return launch_fmha<4>(fp, grid, (cudaStream_t)stream);
     default: return launch_fmha<0>(fp, grid, (cudaStream_t)stream);
   }
 }

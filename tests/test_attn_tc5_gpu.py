@@ -9,12 +9,14 @@ from hi3d_official_b200 import _native, ops  # noqa: E402
 from test_kernels_gpu import DEV, H, close, rnd  # noqa: E402
 
 
-@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2)],
-                ids=["shared-mufu", "shared-emu25", "shared-emu50", "split-mufu", "split-emu25", "split-emu50"], autouse=True)
+@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (2, 4), (3, 0), (3, 1), (3, 3)],
+                ids=["shared-mufu", "shared-emu25", "shared-emu50", "split-mufu", "split-emu25", "split-emu50",
+                     "lean-mufu", "lean-emu25", "lean-emu50", "lean-emu100", "anyorder-mufu", "anyorder-emu25", "anyorder-emu75"],
+                autouse=True)
 def kernel_variant(request):
-    """Every case runs on both kernel variants (shared-row CTA / split half-tile pipelines) with 0 / 25 % / 50 % of the
-    softmax exponentials on the FMA pipe (cubic polynomial) -- the production default is one of the six
-    (attn_tc5.cu FA_VARIANT_DEFAULT, FA_EMU_DEFAULT)."""
+    """Every case runs on every kernel variant (shared-row CTA / split half-tile pipelines / split with the register-lean
+    softmax loop / the same with any-order MMA service) with part of the softmax exponentials on the FMA pipe (cubic
+    polynomial) -- the production default is one of them (attn_tc5.cu FA_VARIANT_DEFAULT, FA_EMU_DEFAULT)."""
     lib = _native.load()
     variant, emu = request.param
     _native.check(lib.hi3d_attention_tc5_set_variant(variant), "set_variant")

@@ -39,11 +39,15 @@ WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_op_utchmma.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
+        "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):        # already exported on the GPU box (ncu -i x.ncu-rep --page raw --csv)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [(w, hdr.index(w)) for w in WANT if w in hdr]
