@@ -75,6 +75,7 @@ _SIGS = {
     "hi3d_attention_d512_tc5": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "hi3d_attention_tc5_set_exp_emulation": (C.c_int, [C.c_int]),
     "hi3d_attention_tc5_set_variant": (C.c_int, [C.c_int]),
+    "hi3d_attention_tc5_set_debug_buffer": (C.c_int, [C.c_void_p]),
     "hi3d_temporal_attention_d64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                               C.c_void_p, C.c_void_p]),
     "hi3d_temporal_attention_d64_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,

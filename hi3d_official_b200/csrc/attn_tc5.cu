@@ -115,6 +115,7 @@ struct FaParams {
   int L, C, heads;
   float scale_log2;
   __half* out;
+  long long* dbg;          // MODE bit 3 (timeline instrumentation of CTA (0,0,0), tiles 16..23): [8 tiles][16 events] of clock64
 };
 
 template <int EMU>
@@ -374,6 +375,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
 //   16384 ex2 per tile) always has a half-tile to work on.
 // =====================================================================================================================
 // MODE bit 0: the MMA warp serves whichever half has its P ready first (polls both barriers) instead of half 0, half 1.
+// MODE bit 2: ping-pong turns between the two halves of a lane quarter (see the softmax loop).
 // MODE bit 1: register-lean softmax loop -- the scores are read in four 16-column chunks and P is only stored once the
 //   whole half-tile has been accepted, so S stays intact in TMEM for the (rare) redo, which re-reads it in two passes;
 //   ~16 registers less at the peak, which is what lets the FMA-pipe exponentials (EMU) fit without spilling.
@@ -387,9 +389,15 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
   const uint32_t sKV = base + FA_TILE_BYTES;                  // stage s: K at sKV + s*2T, V at + T
   const uint32_t bar0 = base + FA_TILE_BYTES * (1 + 2 * FA_STAGES);
   const uint32_t bar_q = bar0;                                // Q landed
-  const uint32_t bar_kv_full = bar0 + 8;                      // [STAGES]
-  const uint32_t bar_kv_empty = bar_kv_full + 8 * FA_STAGES;  // [STAGES]
-  const uint32_t bar_s_full = bar_kv_empty + 8 * FA_STAGES;   // [2 halves]
+  // K and V have their OWN full / empty barriers per stage: a K tile is free as soon as the S MMAs of both halves have
+  // read it (one tile period before the P V MMAs of the same tile retire), so its successor can be loaded a full period
+  // earlier than with one barrier per (K, V) pair -- clock stamps of the paired form showed the MMA warp waiting ~1000
+  // cycles per half-tile for K(j+1) (TMA latency ~1100 cycles against ~470 cycles of lookahead), 40 % of the tile period.
+  const uint32_t bar_k_full = bar0 + 8;                       // [STAGES]
+  const uint32_t bar_k_empty = bar_k_full + 8 * FA_STAGES;    // [STAGES]
+  const uint32_t bar_v_full = bar_k_empty + 8 * FA_STAGES;    // [STAGES]
+  const uint32_t bar_v_empty = bar_v_full + 8 * FA_STAGES;    // [STAGES]
+  const uint32_t bar_s_full = bar_v_empty + 8 * FA_STAGES;    // [2 halves]
   const uint32_t bar_p_full = bar_s_full + 16;                // [2 halves], 4 arrivals each
   const uint32_t bar_o_full = bar_p_full + 16;                // [2 halves]
   const uint32_t tmem_slot = bar_o_full + 32;
@@ -404,7 +412,10 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
 
   if (warp == 0 && lane == 0) {
     mbar_init(bar_q, 1);
-    for (int s = 0; s < FA_STAGES; s++) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
+    for (int s = 0; s < FA_STAGES; s++) {
+      mbar_init(bar_k_full + 8 * s, 1); mbar_init(bar_k_empty + 8 * s, 1);
+      mbar_init(bar_v_full + 8 * s, 1); mbar_init(bar_v_empty + 8 * s, 1);
+    }
     for (int hh = 0; hh < 2; hh++) {
       mbar_init(bar_s_full + 8 * hh, 1);
       mbar_init(bar_p_full + 8 * hh, 4);
@@ -421,6 +432,13 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
   const uint32_t tS0 = tmem_base, tO0 = tmem_base + 128;      // S_h = tS0 + 64 h (P_h aliases its first 32 columns)
+  const bool dbg_cta = (MODE & 8) && p.dbg != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
+#define FA_STAMP(J, E)                                                                     \
+  do {                                                                                     \
+    if constexpr (MODE & 8) {                                                              \
+      if (dbg_cta && lane == 0 && (J) >= 16 && (J) < 24) p.dbg[((J)-16) * 16 + (E)] = clock64(); \
+    }                                                                                      \
+  } while (0)
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -431,12 +449,17 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     __syncwarp();
     for (int j = 0; j < nkv; j++) {
       const int s = j % FA_STAGES;
-      mbar_wait(bar_kv_empty + 8 * s, ((j / FA_STAGES) & 1) ^ 1);
+      const uint32_t ph = ((j / FA_STAGES) & 1) ^ 1;
+      mbar_wait(bar_k_empty + 8 * s, ph);
       if (elect_one()) {
-        const uint32_t full = bar_kv_full + 8 * s;
-        mbar_expect_tx(full, 2 * FA_TILE_BYTES);
-        tma_load_2d(sKV + s * 2 * FA_TILE_BYTES, &p.qkv_map, full, p.C + h * 64, row0 + j * FA_BN);
-        tma_load_2d(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES, &p.qkv_map, full, 2 * p.C + h * 64, row0 + j * FA_BN);
+        mbar_expect_tx(bar_k_full + 8 * s, FA_TILE_BYTES);
+        tma_load_2d(sKV + s * 2 * FA_TILE_BYTES, &p.qkv_map, bar_k_full + 8 * s, p.C + h * 64, row0 + j * FA_BN);
+      }
+      __syncwarp();
+      mbar_wait(bar_v_empty + 8 * s, ph);
+      if (elect_one()) {
+        mbar_expect_tx(bar_v_full + 8 * s, FA_TILE_BYTES);
+        tma_load_2d(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES, &p.qkv_map, bar_v_full + 8 * s, 2 * p.C + h * 64, row0 + j * FA_BN);
       }
       __syncwarp();
     }
@@ -447,7 +470,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
     const uint64_t qd = umma_desc_sw128(sQ);
     mbar_wait(bar_q, 0);
-    mbar_wait(bar_kv_full, 0);
+    mbar_wait(bar_k_full, 0);
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
@@ -458,11 +481,25 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
         for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
         tc_commit(bar_s_full + 8 * hh);
       }
+      tc_commit(bar_k_empty);                                   // K(0) is free once both S(0) have been computed
     }
     __syncwarp();
-    for (int j = 0; j < nkv; j++) {
-      const int s = j % FA_STAGES;
-      const int s1 = (j + 1) % FA_STAGES;
+    // The per-half critical path  P announced -> P V and next S issued  is the kernel's period limiter (clock stamps: 186 +
+    // 349 + 410 cycles of this warp's own latency per half-tile against 256 cycles of tensor work), so everything that does
+    // not depend on P is done before the wait for it: the operand barriers of the tile (V(j), K(j+1) landed long ago) and
+    // the shared-memory descriptors (stage index static: the loop is unrolled by the ring depth).
+    uint64_t kdesc[FA_STAGES][2], vdesc[FA_STAGES][2];
+#pragma unroll
+    for (int s = 0; s < FA_STAGES; s++)
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+        kdesc[s][hh] = umma_desc_sw128(sKV + s * 2 * FA_TILE_BYTES + hh * 8192);
+        vdesc[s][hh] = umma_desc_sw128_mn(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES + hh * 8192);
+      }
+    auto serve_tile = [&](const int j, const int s, const int s1) {
+      const bool more = j + 1 < nkv;
+      mbar_wait(bar_v_full + 8 * s, (j / FA_STAGES) & 1);
+      if (more) mbar_wait(bar_k_full + 8 * s1, ((j + 1) / FA_STAGES) & 1);
       uint32_t pend = 3u;                                       // halves of tile j not yet served (warp-uniform)
       uint32_t polls = 0;
       while (pend) {
@@ -481,24 +518,32 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
           mbar_wait(bar_p_full + 8 * hh, j & 1);                // P_h(j) is in TMEM (aliasing S_h)
         }
         pend &= ~(1u << hh);
-        if (j + 1 < nkv) mbar_wait(bar_kv_full + 8 * s1, ((j + 1) / FA_STAGES) & 1);
+        FA_STAMP(j, 6 + 3 * hh);
         tc_fence_after();
+        FA_STAMP(j, 7 + 3 * hh);
         if (elect_one()) {
-          const uint64_t vd = umma_desc_sw128_mn(sKV + s * 2 * FA_TILE_BYTES + FA_TILE_BYTES + hh * 8192);
+          const uint64_t vd = hh ? vdesc[s][1] : vdesc[s][0];
 #pragma unroll
           for (int k = 0; k < 4; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
             tc_mma_f16_ts(tO0 + 64u * hh, tS0 + 64u * hh + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, (j | k) ? 1u : 0u);
           tc_commit(bar_o_full + 8 * hh);
-          if (pend == 0u) tc_commit(bar_kv_empty + 8 * s);      // both halves of tile j have been issued
-          if (j + 1 < nkv) {                                    // in order behind P_h V_h(j): overwrites the aliased columns
-            const uint64_t kd = umma_desc_sw128(sKV + s1 * 2 * FA_TILE_BYTES + hh * 8192);
+          if (pend == 0u) tc_commit(bar_v_empty + 8 * s);       // both halves' P V of tile j have been issued
+          if (more) {                                           // in order behind P_h V_h(j): overwrites the aliased columns
+            const uint64_t kd = hh ? kdesc[s1][1] : kdesc[s1][0];
 #pragma unroll
             for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
             tc_commit(bar_s_full + 8 * hh);
+            if (pend == 0u) tc_commit(bar_k_empty + 8 * s1);    // both halves' S of tile j+1 have been issued
           }
         }
         __syncwarp();
+        FA_STAMP(j, 8 + 3 * hh);
       }
+    };
+    static_assert(FA_STAGES == 2, "the MMA loop is unrolled by the ring depth");
+    for (int j = 0; j < nkv; j += 2) {
+      serve_tile(j, 0, 1);
+      if (j + 1 < nkv) serve_tile(j + 1, 1, 0);
     }
   } else {
     // ======================= softmax warps: (lane quarter q, key half hf) =======================
@@ -511,16 +556,30 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     const uint32_t b_s = bar_s_full + 8 * hf, b_p = bar_p_full + 8 * hf, b_o = bar_o_full + 8 * hf;
     float m_ref = -INFINITY, l_run = 0.f;        // reference maximum and row sum of THIS half
     if constexpr (MODE & 2) {
+      // MODE bit 2, ping-pong: the two warps of a lane quarter (halves 0 and 1 of this CTA; they share an SM sub-partition
+      // and its MUFU unit) take strict turns in their exponential phase through a pair of 64-thread named barriers.  Without
+      // it the four half-tile pipelines of an SM drift into a convoy: all of them in the exponential phase at once, sharing
+      // the MUFU pipe, then all of them waiting for their MMAs at once (ncu: 40 % of the softmax warps' samples in the
+      // bar_s_full wait while the XU pipe is 68 % busy).  With turns, one half computes while the other half's P V and next
+      // S run on the tensor pipe.
+      const int pp_mine = (hf == 0 ? 5 : 9) + q, pp_other = (hf == 0 ? 9 : 5) + q;
+      if constexpr (MODE & 4) {
+        if (hf == 1) asm volatile("bar.arrive %0, 64;\n" ::"r"(pp_other) : "memory");      // half 0 goes first
+      }
       for (int j = 0; j < nkv; j++) {
         mbar_wait(b_s, j & 1);
         tc_fence_after();
+        if (q == 0) FA_STAMP(j, 3 * hf);
         uint32_t a[16], b[16], pka[16], pkb[16];
         float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         bool redo = (j == 0);
-        if (!redo) {
+        if (redo) {
+          if constexpr (MODE & 4) asm volatile("bar.sync %0, 64;\n" ::"r"(pp_mine) : "memory");
+        } else {
           // optimistic pass against the current reference; nothing is stored until the half-tile has been accepted
           const float nmoff = -(m_ref * c);
           tmem_ld16(tS, a);
+          if constexpr (MODE & 4) asm volatile("bar.sync %0, 64;\n" ::"r"(pp_mine) : "memory");   // my turn
           tmem_ld_wait16(a);
           tmem_ld16(tS + 16, b);
           softmax_exp16<EMU, 0>(a, c, nmoff, pka, rs);
@@ -595,10 +654,16 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
           tmem_st16(tS + 16, pkb);
           l_run = l_run * corr + (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
         }
+        if constexpr (MODE & 4) asm volatile("bar.arrive %0, 64;\n" ::"r"(pp_other) : "memory");   // the partner's turn
+        if (q == 0) FA_STAMP(j, 3 * hf + 1);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(b_p);
+        if (q == 0) FA_STAMP(j, 3 * hf + 2);
+      }
+      if constexpr (MODE & 4) {
+        if (hf == 0) asm volatile("bar.sync %0, 64;\n" ::"r"(pp_mine) : "memory");          // consume half 1's last hand-over
       }
     } else
     for (int j = 0; j < nkv; j++) {
@@ -727,7 +792,7 @@ using namespace hi3d;
 // fraction of the exponentials computed on the FMA pipe: EMU / 4 (0 .. 4; 3 and 4 only in the lean split kernels);
 // -1 = unread (HI3D_FMHA_EMU, else default)
 static int g_fmha_emu = -1;
-constexpr int FA_EMU_DEFAULT = 0;     // measured (profiles/r02_microbench_attn.txt): 1/4 helps the shared-row kernel (+2..18 %), hurts the split one
+constexpr int FA_EMU_DEFAULT = 1;     // measured (profiles/r02_microbench_attn.txt): 1/4 is the optimum of the lean split kernel (837 vs 783 / 794 TFLOP/s for 0 / 2)
 
 extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
   if (quarters < 0 || quarters > 4) { set_error("hi3d_attention_tc5_set_exp_emulation: 0 .. 4 (quarters of the exponentials)"); return -2; }
@@ -736,15 +801,18 @@ extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
 }
 
 // 0 = shared-row kernel, 1 = split half-tile pipelines, 2 = split + register-lean softmax loop, 3 = 2 + the MMA warp serves
-// whichever half is ready; -1 = unread (HI3D_FMHA_VARIANT)
+// whichever half is ready, 4 = 2 + ping-pong turns between the halves; -1 = unread (HI3D_FMHA_VARIANT)
 static int g_fmha_variant = -1;
-constexpr int FA_VARIANT_DEFAULT = 1;  // split pipelines: 783 vs 744 TFLOP/s at L = 16384, 768 vs 726 at L = 4096 x 10 heads
+constexpr int FA_VARIANT_DEFAULT = 2;  // lean split pipelines + 1/4 emulated: 837 vs 774 (split) vs 736 (shared rows) TFLOP/s at L = 16384
 
 extern "C" int hi3d_attention_tc5_set_variant(int variant) {
-  if (variant < 0 || variant > 3) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows), 1 (split), 2 (split, lean), 3 (split, lean, any-order)"); return -2; }
+  if (variant < 0 || variant > 5) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows), 1 (split), 2 (split, lean), 3 (split, lean, any-order), 4 (split, lean, ping-pong)"); return -2; }
   g_fmha_variant = variant;
   return 0;
 }
+
+static long long* g_fmha_dbg = nullptr;      // device buffer of 128 clock64 stamps for variant 5 (tools only)
+extern "C" int hi3d_attention_tc5_set_debug_buffer(void* buf) { g_fmha_dbg = (long long*)buf; return 0; }
 
 template <int EMU, int MODE>
 static int launch_fmha_split(const FaParams& fp, dim3 grid, cudaStream_t st) {
@@ -757,6 +825,11 @@ static int launch_fmha_split(const FaParams& fp, dim3 grid, cudaStream_t st) {
 template <int EMU>
 static int launch_fmha(const FaParams& fp, dim3 grid, cudaStream_t st) {
   static bool attr_done[HI3D_MAX_DEVICES];
+  if (g_fmha_variant == 5) {
+    if constexpr (EMU == 1) return launch_fmha_split<1, 10>(fp, grid, st);
+    else { set_error("hi3d_attention_d64_tc5: the instrumented variant exists for emulation 1/4 only"); return -2; }
+  }
+  if (g_fmha_variant == 4) return launch_fmha_split<EMU, 6>(fp, grid, st);
   if (g_fmha_variant == 3) return launch_fmha_split<EMU, 3>(fp, grid, st);
   if (g_fmha_variant == 2) return launch_fmha_split<EMU, 2>(fp, grid, st);
   if constexpr (EMU <= 2) {
@@ -789,6 +862,7 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   fp.L = L; fp.C = C; fp.heads = heads;
   fp.scale_log2 = scale * 1.4426950408889634f;
   fp.out = (__half*)out;
+  fp.dbg = g_fmha_dbg;
   if (g_fmha_emu < 0) {
     const char* e = getenv("HI3D_FMHA_EMU");
     g_fmha_emu = e ? atoi(e) : FA_EMU_DEFAULT;
@@ -797,7 +871,7 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   if (g_fmha_variant < 0) {
     const char* e = getenv("HI3D_FMHA_VARIANT");
     g_fmha_variant = e ? atoi(e) : FA_VARIANT_DEFAULT;
-    if (g_fmha_variant < 0 || g_fmha_variant > 3) g_fmha_variant = FA_VARIANT_DEFAULT;
+    if (g_fmha_variant < 0 || g_fmha_variant > 5) g_fmha_variant = FA_VARIANT_DEFAULT;
   }
   dim3 grid(L / FA_BM, heads, n_img);
   switch (g_fmha_emu) {

@@ -189,14 +189,19 @@ int hi3d_attention_d64(const void* qkv, int n_img, int L, int heads, float scale
 /* same contract on tcgen05 / TMEM / TMA (S and P*V accumulators in tensor memory, P fed back from TMEM);
  * sequences that are not a multiple of 128 keys are forwarded to hi3d_attention_d64. */
 int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int heads, float scale, void* out, void* stream);
-/* Tuning / test hook of hi3d_attention_d64_tc5: `quarters` / 4 of the softmax exponentials (0, 1 or 2 quarters) are evaluated
- * on the FMA pipe (range reduction + cubic polynomial, relative error 7.5e-5 before the fp16 rounding of P) instead of the
- * MUFU pipe that bounds the kernel.  Process-wide; default from HI3D_FMHA_EMU, else the measured best. */
+/* Tuning / test hook of hi3d_attention_d64_tc5: `quarters` / 4 of the softmax exponentials (0 .. 4; 3 and 4 only with
+ * variants >= 2) are evaluated on the FMA pipe (range reduction + cubic polynomial, relative error 7.5e-5 before the fp16
+ * rounding of P) instead of the MUFU pipe.  Process-wide; default from HI3D_FMHA_EMU, else the measured best. */
 int hi3d_attention_tc5_set_exp_emulation(int quarters);
 /* Kernel variant of hi3d_attention_d64_tc5: 0 = eight softmax warps share one score tile, reference maximum and P barrier
  * per CTA; 1 = the 128 keys of a tile are two independent 64-key pipelines (own score / P columns, accumulator, barriers and
- * per-row state), merged once at the end.  Process-wide; default from HI3D_FMHA_VARIANT, else the measured best. */
+ * per-row state), merged once at the end; 2 = 1 with the register-lean softmax loop (scores read in 16-column chunks, P
+ * stored once the half-tile is accepted by its row sum); 3 = 2 + the MMA warp serves whichever half is ready; 4 = 2 + strict
+ * turns between the halves; 5 = 2 with clock stamps (tools only).  Process-wide; default from HI3D_FMHA_VARIANT, else the
+ * measured best. */
 int hi3d_attention_tc5_set_variant(int variant);
+/* tools/fmha_timeline.py: device buffer of 128 int64 that variant 5 fills with clock64 stamps of one CTA; NULL = off. */
+int hi3d_attention_tc5_set_debug_buffer(void* buf);
 
 /* Temporal self-attention core over the frame axis (T <= 16), head dim 64, for every (clip, pixel, head):
  * token row of (b, t, s) is (b*T + t)*S + s -- the "(b t) s c -> (b s) t c" rearrange of

@@ -9,9 +9,10 @@ from hi3d_official_b200 import _native, ops  # noqa: E402
 from test_kernels_gpu import DEV, H, close, rnd  # noqa: E402
 
 
-@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (2, 4), (3, 0), (3, 1), (3, 3)],
+@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (2, 4), (3, 0), (3, 1), (3, 3), (4, 0), (4, 1), (4, 2)],
                 ids=["shared-mufu", "shared-emu25", "shared-emu50", "split-mufu", "split-emu25", "split-emu50",
-                     "lean-mufu", "lean-emu25", "lean-emu50", "lean-emu100", "anyorder-mufu", "anyorder-emu25", "anyorder-emu75"],
+                     "lean-mufu", "lean-emu25", "lean-emu50", "lean-emu100", "anyorder-mufu", "anyorder-emu25", "anyorder-emu75",
+                     "pingpong-mufu", "pingpong-emu25", "pingpong-emu50"],
                 autouse=True)
 def kernel_variant(request):
     """Every case runs on every kernel variant (shared-row CTA / split half-tile pipelines / split with the register-lean
@@ -22,8 +23,8 @@ def kernel_variant(request):
     _native.check(lib.hi3d_attention_tc5_set_variant(variant), "set_variant")
     _native.check(lib.hi3d_attention_tc5_set_exp_emulation(emu), "set_exp_emulation")
     yield request.param
-    _native.check(lib.hi3d_attention_tc5_set_variant(1), "set_variant")            # back to the production defaults
-    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(0), "set_exp_emulation")
+    _native.check(lib.hi3d_attention_tc5_set_variant(2), "set_variant")            # back to the production defaults
+    _native.check(lib.hi3d_attention_tc5_set_exp_emulation(1), "set_exp_emulation")
 
 
 def ref_attn(qkv, n_img, L, heads):
@@ -41,7 +42,8 @@ def test_attention_tc5(n_img, L, heads, scale):
     out = torch.zeros(n_img * L, C, dtype=H, device=DEV)
     ops.attention_d64(qkv, n_img, L, heads, out, engine="tc5")
     ref = ref_attn(qkv, n_img, L, heads)
-    close(out.view(n_img, L, heads, 64).transpose(1, 2), ref, atol=2e-3, name="fmha tc5")
+    # P is fp16 (2^-11 relative) against fp32 softmax weights: the error bound scales with max |v| (~ 4 * scale)
+    close(out.view(n_img, L, heads, 64).transpose(1, 2), ref, atol=2e-3 * max(1.0, scale), name="fmha tc5")
     out2 = torch.zeros_like(out)
     ops.attention_d64(qkv, n_img, L, heads, out2, engine="mma")
     close(out, out2, atol=8e-3, name="tc5 vs mma")     # two fp16 results: one ulp at |x| ~ 8 is 7.8e-3

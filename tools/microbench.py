@@ -110,15 +110,15 @@ def main():
             out = torch.empty(M, C, dtype=H, device=DEV)
             for e in engines:
                 from hi3d_official_b200 import _native
-                for var in ((0, 1, 2, 3) if e == "tc5" else (0,)):      # shared rows / split / split lean / lean + any-order
+                for var in ((0, 1, 2, 3, 4) if e == "tc5" else (0,)):   # shared rows / split / split lean / lean + any-order / lean + ping-pong
                     for emu in (((0, 1, 2, 3, 4) if var >= 2 else (0, 1, 2)) if e == "tc5" else (0,)):   # quarters of the exps on the FMA pipe
                         _native.load().hi3d_attention_tc5_set_variant(var)
                         _native.load().hi3d_attention_tc5_set_exp_emulation(emu)
                         report(f"{e} spatial attention L={L} heads={heads} variant={var} emu={emu}/4",
                                timeit(lambda: ops.attention_d64(qkv, N, L, heads, out, engine=e), once=args.once),
                                4.0 * N * L * L * C)
-                _native.load().hi3d_attention_tc5_set_variant(1)
-                _native.load().hi3d_attention_tc5_set_exp_emulation(0)
+                _native.load().hi3d_attention_tc5_set_variant(2)
+                _native.load().hi3d_attention_tc5_set_exp_emulation(1)
             report(f"temporal attention S={L} heads={heads}",
                    timeit(lambda: ops.temporal_attention_d64(qkv, 2, T, L, heads, out), once=args.once), 4.0 * N * L * T * C,
                    8.0 * M * C)
