@@ -5,7 +5,7 @@ TOOL=${1:-memcheck}
 mkdir -p gpurun_out
 LOG=gpurun_out/sanitize_${TOOL}.log
 : > $LOG
-for T in "tests/test_gemm_tc5_gpu.py -k 'plain or conv3x3 or temporal'" "tests/test_attn_tc5_gpu.py -k 'split-mufu and (1024 or moving)'" \
+for T in "tests/test_gemm_tc5_gpu.py -k 'plain or conv3x3 or temporal'" "tests/test_attn_tc5_gpu.py -k '(lean-emu25 or split-mufu) and (1024 or moving)'" \
          "tests/test_kernels_gpu.py -k 'groupnorm or layernorm or temporal_attention'"; do
   echo "=== compute-sanitizer --tool $TOOL python -m pytest $T" >> $LOG
   eval timeout 1200 compute-sanitizer --tool $TOOL --error-exitcode 3 --print-limit 20 python -m pytest $T -x -q -m gpu -p no:cacheprovider >> $LOG 2>&1
