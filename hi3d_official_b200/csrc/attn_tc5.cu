@@ -373,12 +373,19 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
 //   -> commit.  In-order execution of the tensor pipe makes P_h V_h(j) read P before S_h(j+1) overwrites the aliased
 //   columns.  With two CTAs per SM this gives four pipelines per SM that drift out of phase, so the MUFU pipe (the bound:
 //   16384 ex2 per tile) always has a half-tile to work on.
+//   Each half-tile pipeline is a serial chain  S ready -> exponentials -> P announced -> MMA warp notices -> P V and next
+//   S issued -> S ready,  so the MMA warp's own latency per half is part of the period (tools/fmha_timeline.py): K and V
+//   have separate barriers (K is released one period before V), the operand barriers are passed BEFORE the wait for P and
+//   the loop is unrolled by the ring depth so that all descriptors are loop-invariant.
+// Template parameters (the production kernel is <EMU = 1, MODE = 2>; the others are kept for the record and the tests):
+//   EMU:        quarters of the exponentials evaluated on the FMA pipe (ex2_emulated2).
+//   MODE bit 0: the MMA warp serves whichever half has its P ready first (polls both barriers) instead of half 0, half 1.
+//   MODE bit 1: register-lean softmax loop -- the scores are read in four 16-column chunks and P is only stored once the
+//     whole half-tile has been accepted (row sum <= 2^12), so S stays intact in TMEM for the (rare) redo, which re-reads it
+//     in two passes; ~16 registers less at the peak, which is what lets the emulated exponentials fit without spilling.
+//   MODE bit 2: ping-pong turns between the two halves of a lane quarter (see the softmax loop).
+//   MODE bit 3: clock64 stamps of one CTA into FaParams::dbg (tools/fmha_timeline.py).
 // =====================================================================================================================
-// MODE bit 0: the MMA warp serves whichever half has its P ready first (polls both barriers) instead of half 0, half 1.
-// MODE bit 2: ping-pong turns between the two halves of a lane quarter (see the softmax loop).
-// MODE bit 1: register-lean softmax loop -- the scores are read in four 16-column chunks and P is only stored once the
-//   whole half-tile has been accepted, so S stays intact in TMEM for the (rare) redo, which re-reads it in two passes;
-//   ~16 registers less at the peak, which is what lets the FMA-pipe exponentials (EMU) fit without spilling.
 template <int EMU, int MODE>
 __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
