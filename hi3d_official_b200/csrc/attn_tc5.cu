@@ -91,14 +91,15 @@ HI3D_DEVINL void softmax_exp32(const uint32_t (&cur)[32], float c, float nmoff, 
 }
 
 // The same for 16 scores -> 8 packed half2 at pk[OFF .. OFF + 8) (register-lean chunks of the split kernel's MODE 2 loop).
-template <int EMU, int OFF>
+// EMU8 = eighths of the exponentials on the FMA pipe (the emulated pairs are spread over the chunk).
+template <int EMU8, int OFF>
 HI3D_DEVINL void softmax_exp16(const uint32_t (&cur)[16], float c, float nmoff, uint32_t (&pk)[16], float2 (&rs)[2]) {
   const float2 c2 = make_float2(c, c), m2 = make_float2(nmoff, nmoff);
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     const float2 x = __ffma2_rn(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), c2, m2);
     float2 pe;
-    if (((i >> 1) & 3) < EMU) pe = ex2_emulated2(x);
+    if ((((i >> 1) * 5) & 7) < EMU8) pe = ex2_emulated2(x);
     else pe = make_float2(ex2_approx_ftz(x.x), ex2_approx_ftz(x.y));
     rs[(i >> 1) & 1] = __fadd2_rn(rs[(i >> 1) & 1], pe);
     pk[OFF + (i >> 1)] = pack_half2(pe.x, pe.y);
@@ -563,6 +564,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     const uint32_t b_s = bar_s_full + 8 * hf, b_p = bar_p_full + 8 * hf, b_o = bar_o_full + 8 * hf;
     float m_ref = -INFINITY, l_run = 0.f;        // reference maximum and row sum of THIS half
     if constexpr (MODE & 2) {
+      // EMU 0 .. 4 = quarters; 5, 6, 7 = 3/8, 1/8, 5/8 (finer steps around the optimum, lean loop only)
+      constexpr int EMU8 = EMU <= 4 ? 2 * EMU : (EMU == 5 ? 3 : (EMU == 6 ? 1 : 5));
       // MODE bit 2, ping-pong: the two warps of a lane quarter (halves 0 and 1 of this CTA; they share an SM sub-partition
       // and its MUFU unit) take strict turns in their exponential phase through a pair of 64-thread named barriers.  Without
       // it the four half-tile pipelines of an SM drift into a convoy: all of them in the exponential phase at once, sharing
@@ -589,15 +592,15 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
           if constexpr (MODE & 4) asm volatile("bar.sync %0, 64;\n" ::"r"(pp_mine) : "memory");   // my turn
           tmem_ld_wait16(a);
           tmem_ld16(tS + 16, b);
-          softmax_exp16<EMU, 0>(a, c, nmoff, pka, rs);
+          softmax_exp16<EMU8, 0>(a, c, nmoff, pka, rs);
           tmem_ld_wait16(b);
           tmem_ld16(tS + 32, a);
-          softmax_exp16<EMU, 8>(b, c, nmoff, pka, rs);
+          softmax_exp16<EMU8, 8>(b, c, nmoff, pka, rs);
           tmem_ld_wait16(a);
           tmem_ld16(tS + 48, b);
-          softmax_exp16<EMU, 0>(a, c, nmoff, pkb, rs);
+          softmax_exp16<EMU8, 0>(a, c, nmoff, pkb, rs);
           tmem_ld_wait16(b);
-          softmax_exp16<EMU, 8>(b, c, nmoff, pkb, rs);
+          softmax_exp16<EMU8, 8>(b, c, nmoff, pkb, rs);
           // Accept the half-tile if its row sum stays below 2^12: then every P <= 2^12 (no fp16 overflow; the relative
           // precision of P does not depend on its scale), and a sum is what the loop computes anyway -- no maximum over the
           // scores at all in the common path (33 FMNMX3 less per 64 scores).  inf / NaN sums fail the test too.
@@ -802,7 +805,7 @@ static int g_fmha_emu = -1;
 constexpr int FA_EMU_DEFAULT = 1;     // measured (profiles/r02_microbench_attn.txt): 1/4 is the optimum of the lean split kernel (837 vs 783 / 794 TFLOP/s for 0 / 2)
 
 extern "C" int hi3d_attention_tc5_set_exp_emulation(int quarters) {
-  if (quarters < 0 || quarters > 4) { set_error("hi3d_attention_tc5_set_exp_emulation: 0 .. 4 (quarters of the exponentials)"); return -2; }
+  if (quarters < 0 || quarters > 7) { set_error("hi3d_attention_tc5_set_exp_emulation: 0 .. 4 (quarters of the exponentials) or 5 / 6 / 7 (3/8, 1/8, 5/8)"); return -2; }
   g_fmha_emu = quarters;
   return 0;
 }
@@ -873,7 +876,7 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   if (g_fmha_emu < 0) {
     const char* e = getenv("HI3D_FMHA_EMU");
     g_fmha_emu = e ? atoi(e) : FA_EMU_DEFAULT;
-    if (g_fmha_emu < 0 || g_fmha_emu > 4) g_fmha_emu = FA_EMU_DEFAULT;
+    if (g_fmha_emu < 0 || g_fmha_emu > 7) g_fmha_emu = FA_EMU_DEFAULT;
   }
   if (g_fmha_variant < 0) {
     const char* e = getenv("HI3D_FMHA_VARIANT");
@@ -886,6 +889,9 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
     case 2: return launch_fmha<2>(fp, grid, (cudaStream_t)stream);
     case 3: return launch_fmha<3>(fp, grid, (cudaStream_t)stream);
     case 4: return launch_fmha<4>(fp, grid, (cudaStream_t)stream);
+    case 5: return launch_fmha<5>(fp, grid, (cudaStream_t)stream);
+    case 6: return launch_fmha<6>(fp, grid, (cudaStream_t)stream);
+    case 7: return launch_fmha<7>(fp, grid, (cudaStream_t)stream);
     default: return launch_fmha<0>(fp, grid, (cudaStream_t)stream);
   }
 }

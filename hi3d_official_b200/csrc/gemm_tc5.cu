@@ -654,6 +654,7 @@ static int launch_tc5_n(int epi, int ew, const T5Params& tp, int smem, int smem_
   if (ew == 16) {      // only the register-light specialisations exist with 16 epilogue warps
     if (epi == EPI_GEGLU) return launch_tc5_one<NCTA, EPI_GEGLU, 16>(tp, smem, smem_total, units, sm_count, st);
     if (epi == EPI_BIAS) return launch_tc5_one<NCTA, EPI_BIAS, 16>(tp, smem, smem_total, units, sm_count, st);
+    if (epi == EPI_RES) return launch_tc5_one<NCTA, EPI_RES, 16>(tp, smem, smem_total, units, sm_count, st);
   }
   switch (epi) {
     case EPI_GEGLU: return launch_tc5_one<NCTA, EPI_GEGLU, 8>(tp, smem, smem_total, units, sm_count, st);
@@ -799,7 +800,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
   }
   // 16 epilogue warps when the epilogue is the bound: short K (main loop of a tile shorter than its epilogue)
   int ew = 8;
-  if ((epi == EPI_GEGLU || epi == EPI_BIAS) && (g_ew_mode == 16 || (g_ew_mode < 0 && p->K <= T5_EW16_MAX_K))) ew = 16;
+  if ((epi == EPI_GEGLU || epi == EPI_BIAS || epi == EPI_RES) && (g_ew_mode == 16 || (g_ew_mode < 0 && p->K <= T5_EW16_MAX_K))) ew = 16;
   const int extra_scr = (ew - T5_EPI_WARPS) * T5_SCR_BYTES;
   const int stage_bytes = T5_A_BYTES + (BN / ncta) * 128;
   int stages = (T5_SMEM_BUDGET - gn_tab_bytes - extra_scr) / stage_bytes;

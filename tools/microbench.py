@@ -102,6 +102,10 @@ def main():
                 report(f"{e} ff2 4C->C C={C} M={M}", timeit(g, once=args.once), g.flops)
                 g = ops.Gemm([ops.SegSpec(x2)], wqkv, qkv, M, engine=e)
                 report(f"{e} qkv C->3C C={C} M={M}", timeit(g, once=args.once), g.flops)
+                wo = rnd(C, C, scale=C ** -0.5)
+                out2 = torch.empty(M, C, dtype=H, device=DEV)
+                g = ops.Gemm([ops.SegSpec(x2)], wo, out2, M, bias=bias, residual=out, engine=e)
+                report(f"{e} proj C->C +res C={C} M={M}", timeit(g, once=args.once), g.flops, 6.0 * M * C)
     if args.only in ("", "attn"):
         for ds, C in ((1, 320), (2, 640), (4, 1280)):
             h = hw // ds
@@ -111,7 +115,7 @@ def main():
             for e in engines:
                 from hi3d_official_b200 import _native
                 for var in ((0, 1, 2, 3, 4) if e == "tc5" else (0,)):   # shared rows / split / split lean / lean + any-order / lean + ping-pong
-                    for emu in (((0, 1, 2, 3, 4) if var >= 2 else (0, 1, 2)) if e == "tc5" else (0,)):   # quarters of the exps on the FMA pipe
+                    for emu in (((0, 6, 1, 5, 2, 7, 3, 4) if var == 2 else (0, 1, 2)) if e == "tc5" else (0,)):   # quarters of the exps on the FMA pipe
                         _native.load().hi3d_attention_tc5_set_variant(var)
                         _native.load().hi3d_attention_tc5_set_exp_emulation(emu)
                         report(f"{e} spatial attention L={L} heads={heads} variant={var} emu={emu}/4",
