@@ -490,7 +490,22 @@ gn_unit_stats_kernel(const __half* __restrict__ x, int C, long long rows_per_ima
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) s[e] = q[e] = 0.f;
-  for (long long r = r0 + rl; r < r1; r += RL) {
+  // four independent 16-byte loads in flight per thread (a read-only stream: memory-level parallelism is the whole game)
+  long long r = r0 + rl;
+  for (; r + 3LL * RL < r1; r += 4LL * RL) {
+    Half8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = ld_stream(base + (r + (long long)u * RL) * C);
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 f = __half22float2(v[u].h[k]);
+        s[2 * k] += f.x; q[2 * k] += f.x * f.x;
+        s[2 * k + 1] += f.y; q[2 * k + 1] += f.y * f.y;
+      }
+  }
+  for (; r < r1; r += RL) {
     const Half8 v = ld_stream(base + r * C);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
