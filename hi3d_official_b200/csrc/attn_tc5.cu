@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_kernel(const __grid_co
 //     in two passes; ~16 registers less at the peak, which is what lets the emulated exponentials fit without spilling.
 //   MODE bit 2: ping-pong turns between the two halves of a lane quarter (see the softmax loop).
 //   MODE bit 3: clock64 stamps of one CTA into FaParams::dbg (tools/fmha_timeline.py).
+//   MODE bit 4: the scores of a half arrive as two 32-key blocks, the first one issued AHEAD of P V (see serve_tile).
 // =====================================================================================================================
 template <int EMU, int MODE>
 __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __grid_constant__ FaParams p) {
@@ -408,7 +409,8 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
   const uint32_t bar_s_full = bar_v_empty + 8 * FA_STAGES;    // [2 halves]
   const uint32_t bar_p_full = bar_s_full + 16;                // [2 halves], 4 arrivals each
   const uint32_t bar_o_full = bar_p_full + 16;                // [2 halves]
-  const uint32_t tmem_slot = bar_o_full + 32;
+  const uint32_t bar_s2_full = bar_o_full + 16;               // [2 halves] (MODE bit 4: scores of the second 32 keys of a half)
+  const uint32_t tmem_slot = bar_s2_full + 32;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - base));
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
       mbar_init(bar_s_full + 8 * hh, 1);
       mbar_init(bar_p_full + 8 * hh, 4);
       mbar_init(bar_o_full + 8 * hh, 1);
+      mbar_init(bar_s2_full + 8 * hh, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -476,6 +479,7 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
     // S_h = Q K_h^T : M 128, N 64, A/B K-major.   O_h += P_h V_h : M 128, N 64, A from TMEM, B MN-major (bit 16).
     const uint32_t idesc_qk = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
     const uint32_t idesc_pv = (1u << 4) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);
+    const uint32_t idesc_qk32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(FA_BM >> 4) << 24);   // N = 32
     const uint64_t qd = umma_desc_sw128(sQ);
     mbar_wait(bar_q, 0);
     mbar_wait(bar_k_full, 0);
@@ -485,9 +489,19 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
       for (int hh = 0; hh < 2; hh++) {
         // keys 64 hh .. 64 hh + 63 of the K tile: 8 swizzle row groups of 1024 bytes further on
         const uint64_t kd = umma_desc_sw128(sKV + hh * 8192);
+        if constexpr (MODE & 16) {
+          // two N = 32 score blocks per half with their own barriers (see serve_tile)
 #pragma unroll
-        for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
-        tc_commit(bar_s_full + 8 * hh);
+          for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk32, k ? 1u : 0u);
+          tc_commit(bar_s_full + 8 * hh);
+#pragma unroll
+          for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh + 32u, qd + (uint64_t)(2 * k), kd + (uint64_t)(256 + 2 * k), idesc_qk32, k ? 1u : 0u);
+          tc_commit(bar_s2_full + 8 * hh);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
+          tc_commit(bar_s_full + 8 * hh);
+        }
       }
       tc_commit(bar_k_empty);                                   // K(0) is free once both S(0) have been computed
     }
@@ -531,17 +545,43 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
         FA_STAMP(j, 7 + 3 * hh);
         if (elect_one()) {
           const uint64_t vd = hh ? vdesc[s][1] : vdesc[s][0];
+          const uint64_t kd = hh ? kdesc[s1][1] : kdesc[s1][0];
+          if constexpr (MODE & 16) {
+            // MODE bit 4: the 64 score columns of a half are two 32-column blocks that swap roles every tile.  P(j) sits in
+            // block X = 32 (j & 1) (where the scores of the half's first 32 keys were); the other block Y was read completely
+            // before P was announced, so the scores of the first 32 keys of tile j+1 go there IMMEDIATELY -- ahead of P V(j) --
+            // and the softmax warps can start tile j+1 one P V + half an S earlier; the second 32 keys follow behind P V(j)
+            // into block X.  Three commits per half-tile: s_full (first block), o_full, s2_full (second block).
+            const uint32_t X = 32u * (uint32_t)s, Y = 32u - X;
+            if (more) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh + Y, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk32, k ? 1u : 0u);
+              tc_commit(bar_s_full + 8 * hh);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              tc_mma_f16_ts(tO0 + 64u * hh, tS0 + 64u * hh + X + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, (j | k) ? 1u : 0u);
+            tc_commit(bar_o_full + 8 * hh);
+            if (pend == 0u) tc_commit(bar_v_empty + 8 * s);
+            if (more) {
+#pragma unroll
+              for (int k = 0; k < 4; k++)   // keys 32 .. 63 of the half: 4 swizzle row groups (4096 B) further on
+                tc_mma_f16(tS0 + 64u * hh + X, qd + (uint64_t)(2 * k), kd + (uint64_t)(256 + 2 * k), idesc_qk32, k ? 1u : 0u);
+              tc_commit(bar_s2_full + 8 * hh);
+              if (pend == 0u) tc_commit(bar_k_empty + 8 * s1);
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < 4; k++)   // 16 keys per MMA: P advances 8 packed columns, V advances 16 rows (2048 B)
             tc_mma_f16_ts(tO0 + 64u * hh, tS0 + 64u * hh + (uint32_t)(8 * k), vd + (uint64_t)(128 * k), idesc_pv, (j | k) ? 1u : 0u);
           tc_commit(bar_o_full + 8 * hh);
           if (pend == 0u) tc_commit(bar_v_empty + 8 * s);       // both halves' P V of tile j have been issued
           if (more) {                                           // in order behind P_h V_h(j): overwrites the aliased columns
-            const uint64_t kd = hh ? kdesc[s1][1] : kdesc[s1][0];
 #pragma unroll
             for (int k = 0; k < 4; k++) tc_mma_f16(tS0 + 64u * hh, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
             tc_commit(bar_s_full + 8 * hh);
             if (pend == 0u) tc_commit(bar_k_empty + 8 * s1);    // both halves' S of tile j+1 have been issued
+          }
           }
         }
         __syncwarp();
@@ -576,10 +616,15 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
       if constexpr (MODE & 4) {
         if (hf == 1) asm volatile("bar.arrive %0, 64;\n" ::"r"(pp_other) : "memory");      // half 0 goes first
       }
+      const uint32_t b_s2 = bar_s2_full + 8 * hf;
       for (int j = 0; j < nkv; j++) {
         mbar_wait(b_s, j & 1);
         tc_fence_after();
         if (q == 0) FA_STAMP(j, 3 * hf);
+        // block X holds the scores of the half's first 32 keys and later P; block Y the second 32 keys (MODE bit 4: the blocks
+        // swap roles every tile and Y is only valid after its own barrier; otherwise X = 0, Y = 32)
+        const uint32_t tX = (MODE & 16) ? tS + 32u * (uint32_t)(j & 1) : tS;
+        const uint32_t tY = (MODE & 16) ? tS + 32u - 32u * (uint32_t)(j & 1) : tS + 32u;
         uint32_t a[16], b[16], pka[16], pkb[16];
         float2 rs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         bool redo = (j == 0);
@@ -588,16 +633,17 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
         } else {
           // optimistic pass against the current reference; nothing is stored until the half-tile has been accepted
           const float nmoff = -(m_ref * c);
-          tmem_ld16(tS, a);
+          tmem_ld16(tX, a);
           if constexpr (MODE & 4) asm volatile("bar.sync %0, 64;\n" ::"r"(pp_mine) : "memory");   // my turn
           tmem_ld_wait16(a);
-          tmem_ld16(tS + 16, b);
+          tmem_ld16(tX + 16, b);
           softmax_exp16<EMU8, 0>(a, c, nmoff, pka, rs);
           tmem_ld_wait16(b);
-          tmem_ld16(tS + 32, a);
+          if constexpr (MODE & 16) { mbar_wait(b_s2, j & 1); tc_fence_after(); }
+          tmem_ld16(tY, a);
           softmax_exp16<EMU8, 8>(b, c, nmoff, pka, rs);
           tmem_ld_wait16(a);
-          tmem_ld16(tS + 48, b);
+          tmem_ld16(tY + 16, b);
           softmax_exp16<EMU8, 0>(a, c, nmoff, pkb, rs);
           tmem_ld_wait16(b);
           softmax_exp16<EMU8, 8>(b, c, nmoff, pkb, rs);
@@ -608,23 +654,24 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
           redo = __any_sync(0xffffffffu, !(tsum <= 4096.0f)) != 0;
           if (!redo) {
             l_run += tsum;
-            tmem_st16(tS, pka);
-            tmem_st16(tS + 16, pkb);
+            tmem_st16(tX, pka);
+            tmem_st16(tX + 16, pkb);
           }
         }
         if (redo) {
           // the reference moves (always on the first tile).  S is intact in TMEM: pass 1 = row maximum, pass 2 = P.
           float mxa[4] = {m_ref, m_ref, m_ref, m_ref};
+          if constexpr (MODE & 16) { mbar_wait(b_s2, j & 1); tc_fence_after(); }
           {
-            tmem_ld16(tS, a);
+            tmem_ld16(tX, a);
             tmem_ld_wait16(a);
-            tmem_ld16(tS + 16, b);
+            tmem_ld16(tX + 16, b);
             rowmax16(a, mxa);
             tmem_ld_wait16(b);
-            tmem_ld16(tS + 32, a);
+            tmem_ld16(tY, a);
             rowmax16(b, mxa);
             tmem_ld_wait16(a);
-            tmem_ld16(tS + 48, b);
+            tmem_ld16(tY + 16, b);
             rowmax16(a, mxa);
             tmem_ld_wait16(b);
             rowmax16(b, mxa);
@@ -647,21 +694,21 @@ __global__ void __launch_bounds__(FA_THREADS, 2) fmha_tc5_split_kernel(const __g
           rs[0] = make_float2(0.f, 0.f);
           rs[1] = make_float2(0.f, 0.f);
           const float nmoff = -(mx * c);
-          // P chunk k (8 packed columns) lands on score columns [8k, 8k + 8): always columns that were read before
-          tmem_ld16(tS, a);
+          // P is stored (over block X) after every score of the half-tile has been read
+          tmem_ld16(tX, a);
           tmem_ld_wait16(a);
-          tmem_ld16(tS + 16, b);
+          tmem_ld16(tX + 16, b);
           softmax_exp16<0, 0>(a, c, nmoff, pka, rs);
           tmem_ld_wait16(b);
-          tmem_ld16(tS + 32, a);
+          tmem_ld16(tY, a);
           softmax_exp16<0, 8>(b, c, nmoff, pka, rs);
           tmem_ld_wait16(a);
-          tmem_ld16(tS + 48, b);
+          tmem_ld16(tY + 16, b);
           softmax_exp16<0, 0>(a, c, nmoff, pkb, rs);
           tmem_ld_wait16(b);
           softmax_exp16<0, 8>(b, c, nmoff, pkb, rs);
-          tmem_st16(tS, pka);
-          tmem_st16(tS + 16, pkb);
+          tmem_st16(tX, pka);
+          tmem_st16(tX + 16, pkb);
           l_run = l_run * corr + (rs[0].x + rs[0].y) + (rs[1].x + rs[1].y);
         }
         if constexpr (MODE & 4) asm volatile("bar.arrive %0, 64;\n" ::"r"(pp_other) : "memory");   // the partner's turn
@@ -816,7 +863,7 @@ static int g_fmha_variant = -1;
 constexpr int FA_VARIANT_DEFAULT = 2;  // lean split pipelines + 1/4 emulated: 837 vs 774 (split) vs 736 (shared rows) TFLOP/s at L = 16384
 
 extern "C" int hi3d_attention_tc5_set_variant(int variant) {
-  if (variant < 0 || variant > 5) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows), 1 (split), 2 (split, lean), 3 (split, lean, any-order), 4 (split, lean, ping-pong)"); return -2; }
+  if (variant < 0 || variant > 6) { set_error("hi3d_attention_tc5_set_variant: 0 (shared rows), 1 (split), 2 (split, lean), 3 (split, lean, any-order), 4 (split, lean, ping-pong)"); return -2; }
   g_fmha_variant = variant;
   return 0;
 }
@@ -839,6 +886,7 @@ static int launch_fmha(const FaParams& fp, dim3 grid, cudaStream_t st) {
     if constexpr (EMU == 1) return launch_fmha_split<1, 10>(fp, grid, st);
     else { set_error("hi3d_attention_d64_tc5: the instrumented variant exists for emulation 1/4 only"); return -2; }
   }
+  if (g_fmha_variant == 6) return launch_fmha_split<EMU, 18>(fp, grid, st);
   if (g_fmha_variant == 4) return launch_fmha_split<EMU, 6>(fp, grid, st);
   if (g_fmha_variant == 3) return launch_fmha_split<EMU, 3>(fp, grid, st);
   if (g_fmha_variant == 2) return launch_fmha_split<EMU, 2>(fp, grid, st);
@@ -881,7 +929,7 @@ extern "C" int hi3d_attention_d64_tc5(const void* qkv, int n_img, int L, int hea
   if (g_fmha_variant < 0) {
     const char* e = getenv("HI3D_FMHA_VARIANT");
     g_fmha_variant = e ? atoi(e) : FA_VARIANT_DEFAULT;
-    if (g_fmha_variant < 0 || g_fmha_variant > 5) g_fmha_variant = FA_VARIANT_DEFAULT;
+    if (g_fmha_variant < 0 || g_fmha_variant > 6) g_fmha_variant = FA_VARIANT_DEFAULT;
   }
   dim3 grid(L / FA_BM, heads, n_img);
   switch (g_fmha_emu) {

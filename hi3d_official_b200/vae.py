@@ -167,21 +167,21 @@ class _VAEPlan:
             self._gemm(lambda: [ops.SegSpec(o.t)], Wo, out, M, bias=bo, residual=x, **self._track(out, C, L))
             return out
         # small / odd sizes (L not a multiple of 128) and the mma.sync engine: scores through the GEMM engine, one image at a
-        # time (an L x L fp16 buffer -- fine for the tiny test shapes this path still serves)
+        # time (an L x L fp16 buffer of SCALED logits -- fine for the tiny test shapes this path still serves)
         if L % 64:
             raise NotImplementedError(f"VAE attention needs (H/8)*(W/8) % 64 == 0, got {L}")
         g, q, k, v, o = (A.want(t, M, C) for t in ("gn", "q", "k", "v", "att"))
         S, vt = A.want("scores", L, L), A.want("vt", C, L)
         out = self._nxt(M, C)
         self._gn(x, pre + "norm", L, g, silu=False)
-        for nm, dst in (("q", q), ("k", k), ("v", v)):
+        for nm, dst in (("q_scaled", q), ("k", k), ("v", v)):
             Wt, b = self.P[pre + nm]
             self._gemm(lambda: [ops.SegSpec(g.t)], Wt, dst, M, bias=b)
         for i in range(n):
             sl = slice(i * L, (i + 1) * L)
             self._call(lambda sl=sl: ops.transpose(v.t[sl], L, C, C, vt.t))
             self._gemm(lambda sl=sl: [ops.SegSpec(q.t[sl])], lambda sl=sl: k.t[sl], S, L)
-            self._call(lambda: ops.softmax_rows(S.t, L, L, float(C) ** -0.5))
+            self._call(lambda: ops.softmax_rows(S.t, L, L, 1.0))
             self._gemm(lambda: [ops.SegSpec(S.t)], vt, lambda sl=sl: o.t[sl], L)
         Wo, bo = self.P[pre + "proj_out"]
         self._gemm(lambda: [ops.SegSpec(o.t)], Wo, out, M, bias=bo, residual=x, **self._track(out, C, L))
@@ -391,6 +391,11 @@ class AutoencoderKL(nn.Module):
             if pre + "q" in P:
                 P[pre + "qkv"] = (torch.cat([P[pre + n_][0] for n_ in "qkv"], 0).contiguous(),
                                   torch.cat([P[pre + n_][1] for n_ in "qkv"], 0).contiguous())
+                # GEMM-softmax-GEMM fallback (L % 128 != 0): its L x L score buffer is fp16, so the softmax scale
+                # C^-0.5 is folded into the q projection -- the stored logits are the scaled ones, as in the reference
+                Wq_, bq_ = P[pre + "q"]
+                sc = float(Wq_.shape[0]) ** -0.5
+                P[pre + "q_scaled"] = ((Wq_.float() * sc).to(Wq_.dtype).contiguous(), (bq_ * sc).contiguous())
         self._packed = P
         return P
 

@@ -197,7 +197,8 @@ int hi3d_attention_tc5_set_exp_emulation(int quarters);
  * per CTA; 1 = the 128 keys of a tile are two independent 64-key pipelines (own score / P columns, accumulator, barriers and
  * per-row state), merged once at the end; 2 = 1 with the register-lean softmax loop (scores read in 16-column chunks, P
  * stored once the half-tile is accepted by its row sum); 3 = 2 + the MMA warp serves whichever half is ready; 4 = 2 + strict
- * turns between the halves; 5 = 2 with clock stamps (tools only).  Process-wide; default from HI3D_FMHA_VARIANT, else the
+ * turns between the halves; 5 = 2 with clock stamps (tools only); 6 = 2 with the scores of a half issued as two 32-key blocks,
+ * the first one ahead of P V.  Process-wide; default from HI3D_FMHA_VARIANT, else the
  * measured best. */
 int hi3d_attention_tc5_set_variant(int variant);
 /* tools/fmha_timeline.py: device buffer of 128 int64 that variant 5 fills with clock64 stamps of one CTA; NULL = off. */

@@ -9,10 +9,11 @@ from hi3d_official_b200 import _native, ops  # noqa: E402
 from test_kernels_gpu import DEV, H, close, rnd  # noqa: E402
 
 
-@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (2, 4), (2, 5), (2, 6), (3, 0), (3, 1), (3, 3), (4, 0), (4, 1), (4, 2)],
+@pytest.fixture(params=[(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (2, 4), (2, 5), (2, 6), (3, 0), (3, 1), (3, 3), (4, 0), (4, 1), (4, 2), (6, 0), (6, 1), (6, 5)],
                 ids=["shared-mufu", "shared-emu25", "shared-emu50", "split-mufu", "split-emu25", "split-emu50",
                      "lean-mufu", "lean-emu25", "lean-emu50", "lean-emu100", "lean-emu37", "lean-emu12", "anyorder-mufu", "anyorder-emu25", "anyorder-emu75",
-                     "pingpong-mufu", "pingpong-emu25", "pingpong-emu50"],
+                     "pingpong-mufu", "pingpong-emu25", "pingpong-emu50",
+                     "blocks-mufu", "blocks-emu25", "blocks-emu37"],
                 autouse=True)
 def kernel_variant(request):
     """Every case runs on every kernel variant (shared-row CTA / split half-tile pipelines / split with the register-lean

@@ -114,8 +114,8 @@ def main():
             out = torch.empty(M, C, dtype=H, device=DEV)
             for e in engines:
                 from hi3d_official_b200 import _native
-                for var in ((0, 1, 2, 3, 4) if e == "tc5" else (0,)):   # shared rows / split / split lean / lean + any-order / lean + ping-pong
-                    for emu in (((0, 6, 1, 5, 2, 7, 3, 4) if var == 2 else (0, 1, 2)) if e == "tc5" else (0,)):   # quarters of the exps on the FMA pipe
+                for var in ((0, 1, 2, 3, 4, 6) if e == "tc5" else (0,)):   # shared rows / split / split lean / lean + any-order / lean + ping-pong
+                    for emu in (((0, 6, 1, 5, 2, 7, 3, 4) if var == 2 else ((0, 1, 5, 2) if var == 6 else (0, 1, 2))) if e == "tc5" else (0,)):   # quarters of the exps on the FMA pipe
                         _native.load().hi3d_attention_tc5_set_variant(var)
                         _native.load().hi3d_attention_tc5_set_exp_emulation(emu)
                         report(f"{e} spatial attention L={L} heads={heads} variant={var} emu={emu}/4",
