@@ -69,6 +69,7 @@ struct T5Params {
   // GroupNorm statistics of the output (hi3d_gemm_params::gn_stats), added to the global table from the epilogue registers
   float* gn_stats;
   int gn_unit, gn_rows, gn_units, gn_nimg;   // channels per unit, GEMM-grid rows per image, units per image (N / unit), images
+  int gelu_poly;                             // GEGLU gate: 1 = MUFU-free polynomial erf (gelu_poly2), 0 = Abramowitz-Stegun form
 };
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 + MUFU error, far
@@ -113,6 +114,40 @@ HI3D_DEVINL float2 gelu_fast2(float2 x) {
   const float2 ex = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
   const float2 em = __ffma2_rn(p, ex, make_float2(-1.0f, -1.0f));          // -(erf|z|), <= 0
   const float2 e = make_float2(copysignf(em.x, x.x), copysignf(em.y, x.y));  // erf(x / sqrt 2)
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, e, hx);
+}
+
+// The same gate without the MUFU pipe: erf(z) = z P(w), w = 2 z^2 / Z^2 - 1, on |z| <= Z = 3.4 (weighted least-squares fit
+// of degree 10 in w; beyond Z the clamp makes erf = +-(1 - 1.5e-6)).  |gelu error| <= 5e-6 over all x (checked in fp32
+// against the exact function, tools/gelu_fit.py) -- two orders below the fp16 rounding of the GEGLU output.  The clamp is
+// a saturating FMA: t = sat(z / 2Z + 1/2), z_c = 2Z t - Z.  18 issue slots per pair of gates, none of them MUFU
+// (gelu_fast2: 21 including 4 MUFU).  Measured on the GEGLU C = 320 GEMM: 1.029 ms with either gate -- the epilogue is bound by
+// dependency and shared-memory latency spread over the whole chunk (profiles/r02_ncu_gemm_epilogue_notes.txt), not by the
+// gate's arithmetic -- so gelu_fast2 stays the default and this one is selectable (HI3D_TC5_GELU=poly).
+HI3D_DEVINL float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+HI3D_DEVINL float2 gelu_poly2(float2 x) {
+  constexpr float Z = 3.4f;
+  const float kz = 0.70710678118654752f * 0.5f / Z;
+  const float2 t = make_float2(fma_sat(x.x, kz, 0.5f), fma_sat(x.y, kz, 0.5f));
+  const float2 zc = __ffma2_rn(t, make_float2(2.f * Z, 2.f * Z), make_float2(-Z, -Z));
+  const float2 zs = __fmul2_rn(zc, make_float2(2.f / (Z * Z), 2.f / (Z * Z)));
+  const float2 w = __ffma2_rn(zs, zc, make_float2(-1.f, -1.f));
+  float2 p = __ffma2_rn(make_float2(0.004088203888386488f, 0.004088203888386488f), w, make_float2(-0.012048999778926373f, -0.012048999778926373f));
+  p = __ffma2_rn(p, w, make_float2(0.015636751428246498f, 0.015636751428246498f));
+  p = __ffma2_rn(p, w, make_float2(-0.021256500855088234f, -0.021256500855088234f));
+  p = __ffma2_rn(p, w, make_float2(0.03925583139061928f, 0.03925583139061928f));
+  p = __ffma2_rn(p, w, make_float2(-0.06293924897909164f, -0.06293924897909164f));
+  p = __ffma2_rn(p, w, make_float2(0.08708704262971878f, 0.08708704262971878f));
+  p = __ffma2_rn(p, w, make_float2(-0.11474799364805222f, -0.11474799364805222f));
+  p = __ffma2_rn(p, w, make_float2(0.14947132766246796f, 0.14947132766246796f));
+  p = __ffma2_rn(p, w, make_float2(-0.20609460771083832f, -0.20609460771083832f));
+  p = __ffma2_rn(p, w, make_float2(0.41566580533981323f, 0.41566580533981323f));
+  const float2 e = __fmul2_rn(zc, p);                      // erf(x / sqrt 2)
   const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return __ffma2_rn(hx, e, hx);
 }
@@ -437,7 +472,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc5_kernel(const __grid_
           Half8 o8[2];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            const float2 gl = gelu_fast2(make_float2(f[2 * j + 1], f[2 * j + 3]));
+            const float2 gin = make_float2(f[2 * j + 1], f[2 * j + 3]);
+            const float2 gl = p.gelu_poly ? gelu_poly2(gin) : gelu_fast2(gin);
             const float2 o = __fmul2_rn(make_float2(f[2 * j], f[2 * j + 2]), gl);
             o8[j >> 3].h[(j & 7) >> 1] = __floats2half2_rn(o.x, o.y);
           }
@@ -619,10 +655,12 @@ static bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 static int g_pair_mode = -2;      // -2 unread, -1 auto, 0 single CTA, 1 CTA pairs
 static int g_dbg = -1;            // -1 unread
 static int g_ew_mode = -2;        // -2 unread, -1 auto, 8 / 16 forced (HI3D_TC5_EW)
+static int g_gelu_poly = -1;      // -1 unread; HI3D_TC5_GELU=poly selects the MUFU-free gate (measured: same speed, so the default stays A-S)
 constexpr int T5_EW16_MAX_K = 640;
 static void read_env_once() {
   if (g_pair_mode == -2) { const char* e = getenv("HI3D_TC5_PAIR"); g_pair_mode = e ? atoi(e) : -1; }
   if (g_dbg < 0) { const char* e = getenv("HI3D_TC5_DBG"); g_dbg = e ? atoi(e) : 0; }
+  if (g_gelu_poly < 0) { const char* e = getenv("HI3D_TC5_GELU"); g_gelu_poly = (e && e[0] == 'p') ? 1 : 0; }
   if (g_ew_mode == -2) { const char* e = getenv("HI3D_TC5_EW"); g_ew_mode = e ? atoi(e) : -1; if (g_ew_mode != 8 && g_ew_mode != 16) g_ew_mode = -1; }
 }
 
@@ -789,6 +827,7 @@ extern "C" int hi3d_gemm_tc5(const hi3d_gemm_params* p, void* stream) {
     tp.gn_stats = p->gn_stats; tp.gn_unit = p->gn_unit; tp.gn_rows = p->gn_rows;
     tp.gn_units = p->N / p->gn_unit; tp.gn_nimg = p->M / p->gn_rows;
   }
+  tp.gelu_poly = g_gelu_poly;
   // epilogue specialisation and epilogue warp count (decided here: the scratch of 16 warps comes out of the stage budget)
   int epi = EPI_GENERIC;
   const bool has_res = p->residual != nullptr, has_blend = p->blend_x != nullptr, has_gn = p->gn_stats != nullptr;
