@@ -1,5 +1,11 @@
 // Spatial self-attention core (head dim 64) on tcgen05 / TMEM / TMA.
 //
+// Two kernels live here.  The PRODUCTION kernel is fmha_tc5_split_kernel<EMU = 1, MODE = 2> further down (two independent
+// 64-key pipelines per CTA, register-lean softmax loop, a quarter of the exponentials on the FMA pipe, separate K / V
+// rings; 880 TFLOP/s at L = 16384).  fmha_tc5_kernel right below is its predecessor (eight softmax warps sharing one score
+// tile), kept selectable (hi3d_attention_tc5_set_variant(0)) because the measurements in DESIGN.md refer to it.  Its
+// description follows.
+//
 // One CTA = 128 queries of one (image, head).  Per 128-key tile:
 //   S = Q K^T        tcgen05.mma, A = Q (smem, K-major), B = K tile (smem, K-major)      -> TMEM S[b]  (128 fp32 cols)
 //   softmax          4 warps, one thread per query row.  The kernel is bound by TMEM READ bandwidth (S is 64 KB per
