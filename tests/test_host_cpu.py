@@ -246,3 +246,29 @@ def test_video_io_and_svd_widening(tmp_path):
     assert le.shape[1] == 512 and not bool(le[:, :256].any()) and torch.equal(le[:, 256:], l1[:, 512:])
     same = [k for k in sd1 if k not in ("input_blocks.0.0.weight", "label_emb.0.0.weight")]
     assert all(torch.equal(wide[pre + k], sd1[k]) for k in same)
+
+
+def test_docs_point_at_existing_profiles():
+    """Every `profiles/r0N_*` file the documents cite exists (brace lists and globs expanded)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def expand(name):
+        m = re.search(r"\{([^}]*)\}", name)
+        if not m:
+            return [name]
+        out = []
+        for alt in m.group(1).split(","):
+            out += expand(name[:m.start()] + alt + name[m.end():])
+        return out
+
+    missing = []
+    for doc in ("DESIGN.md", "README.md", "profiles/README.md", "INTEGRATION.md"):
+        text = open(os.path.join(root, doc)).read()
+        for m in re.finditer(r"`((?:profiles/)?r0[12]_[A-Za-z0-9_{},.*-]+)`", text):
+            ref = m.group(1) if m.group(1).startswith("profiles/") else "profiles/" + m.group(1)
+            for f in expand(ref):
+                if not glob.glob(os.path.join(root, f)) and not glob.glob(os.path.join(root, f) + "*"):
+                    missing.append((doc, f))
+    assert not missing, missing
