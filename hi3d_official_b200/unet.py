@@ -294,7 +294,26 @@ class _Plan:
         self.peer = None
         if self.exchange_mode == "peer":
             from . import peer as _peer
-            self.peer = _peer.get_group(self.rank, self.world, self.dev)
+            forced = "HI3D_SHARD_EXCHANGE" in os.environ
+            try:
+                self.peer = _peer.get_group(self.rank, self.world, self.dev)
+                ok = 1
+            except Exception as e:          # no peer-to-peer access between the GPUs of this box (IPC open fails on every rank)
+                if forced:
+                    raise
+                ok, why = 0, e
+            if not forced:
+                # the ranks must agree: one rank on NCCL and another on peer memory would deadlock
+                import torch.distributed as _dist
+                flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+                _dist.all_reduce(flag, op=_dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    if self.rank == 0:
+                        import sys
+                        print("hi3d: peer-memory exchange unavailable on this box"
+                              + (f" ({why})" if not ok else " (on another rank)") + "; frame sharding falls back to NCCL exchanges",
+                              file=sys.stderr)
+                    self.peer, self.exchange_mode = None, "nccl"
         self.arena = Arena(self.dev, self.peer, ("qkv", "att", "ghalo") if self.peer is not None else ())
         # GroupNorm statistics from the producing GEMM epilogues (hi3d_gemm_params::gn_stats): every GroupNorm is ONE launch
         # (apply); HI3D_GN_FUSED=0 keeps the separate statistics pass (stats + finalize + apply)
